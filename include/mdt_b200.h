@@ -1,0 +1,134 @@
+/*
+ * mdt_b200.h — C-ABI of libmdt_b200.so: the B200 (sm_100a) drop-in for the native ops of
+ * MIC-DKFZ/medicaldetectiontoolkit's detection hot path.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no framework types; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;
+ *   - the caller owns all memory including scratch ("workspace"); query sizes with *_workspace_bytes;
+ *   - work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no host sync inside;
+ *   - return value: 0 = success, <0 = MDT_E* argument error, >0 = cudaError_t of the failed launch.
+ *     Nothing ever calls exit() (the reference's launchers do: roi_align_3D/.../crop_and_resize_kernel.cu:326-331).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the reference root).
+ */
+#ifndef MDT_B200_H
+#define MDT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDT_OK 0
+#define MDT_EINVAL (-1)     /* bad argument (null pointer, negative size, unsupported shape) */
+#define MDT_EWORKSPACE (-2) /* workspace too small */
+#define MDT_EUNSUPPORTED (-3)
+#define MDT_EDRIVER (-4)    /* driver entry point (tensor-map encode) unavailable or failed */
+
+int mdt_version(void);
+/* human-readable text for a return code of any entry point */
+const char *mdt_error_string(int code);
+
+/* ------------------------------------------------------------------ NMS ------------------------------------------------------------------
+ * replaces: cuda_functions/nms_3D/src/cuda/nms_kernel.h:11-12  `void _nms(int boxes_num, float* boxes_dev, unsigned long long* mask_dev, float thresh)`
+ *           cuda_functions/nms_3D/src/nms_cuda.h:1             `int gpu_nms(THLongTensor* keep, THLongTensor* num_out, THCudaTensor* boxes, float thresh)`
+ *           (2D twins under cuda_functions/nms_2D/)
+ * boxes are sorted by descending score: 3D rows = (y1,x1,y2,x2,z1,z2,score) [N,7] f32, 2D rows = (y1,x1,y2,x2,score) [N,5] f32, contiguous.
+ * IoU uses +1 extents and the strict `>` of nms_kernel.cu:16-28,71.
+ */
+
+/* bitmask only — same contract as the reference `_nms` plus stream/status; mask is [N, ceil(N/64)] u64, fully written */
+int mdt_nms_mask_3d(int boxes_num, const float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh, void *stream);
+int mdt_nms_mask_2d(int boxes_num, const float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh, void *stream);
+
+/* fused: bitmask + ON-DEVICE greedy reduction (replaces the D2H copy + host loop of nms_cuda.c:33-61).
+ * keep_out [N] int64: first *num_out entries are the kept row indices (into the sorted input), ascending; num_out [1] int32 (device). */
+size_t mdt_nms_workspace_bytes(int boxes_num);
+int mdt_nms_3d(const float *boxes_dev, int boxes_num, float nms_overlap_thresh, void *workspace, size_t workspace_bytes,
+               int64_t *keep_out, int *num_out, void *stream);
+int mdt_nms_2d(const float *boxes_dev, int boxes_num, float nms_overlap_thresh, void *workspace, size_t workspace_bytes,
+               int64_t *keep_out, int *num_out, void *stream);
+
+/* --------------------------------------------------------------- RoIAlign ----------------------------------------------------------------
+ * replaces: cuda_functions/roi_align_3D/roi_align/src/cuda/crop_and_resize_kernel.h:8-18 (CropAndResizeLaucher / CropAndResizeBackpropImageLaucher)
+ *           and the 2D twins. Same argument order; added: element strides of the image (so channels-last maps need no copy) and int status.
+ * image  logical [batch, depth(C), H, W, Z] f32 with element strides img_strides[5] (2D: [batch, C, H, W], img_strides[4])
+ * boxes  [num_boxes, 6] f32 normalised (y1,x1,y2,x2,z1,z2)   (2D: [num_boxes,4])
+ * box_ind[num_boxes] int32 in [0,batch); out-of-range => that crop stays zero (crop_and_resize_kernel.cu:43-47 + crop_and_resize_gpu.c:27)
+ * crops  logical [num_boxes, C, ch, cw, cz] f32 with element strides crop_strides[5]; fully written (zeros for bad box_ind).
+ * extrapolation_value is accepted and ignored, as in the reference GPU kernel.
+ */
+int mdt_crop_and_resize_3d_forward(const float *image, const int64_t *img_strides_host, const float *boxes, const int *box_ind, int num_boxes,
+                                   int batch, int image_height, int image_width, int image_zdepth, int crop_height, int crop_width,
+                                   int crop_zdepth, int depth, float extrapolation_value, float *crops, const int64_t *crop_strides_host,
+                                   void *stream);
+/* grads_image must be zero-filled by the caller OR pass zero_init=1 to have the library memset it (contiguous-in-memory extent given by image_numel) */
+int mdt_crop_and_resize_3d_backward(const float *grads, const int64_t *grad_strides_host, const float *boxes, const int *box_ind, int num_boxes,
+                                    int batch, int image_height, int image_width, int image_zdepth, int crop_height, int crop_width,
+                                    int crop_zdepth, int depth, float *grads_image, const int64_t *img_strides_host, int zero_init,
+                                    int64_t image_numel, void *stream);
+int mdt_crop_and_resize_2d_forward(const float *image, const int64_t *img_strides_host, const float *boxes, const int *box_ind, int num_boxes,
+                                   int batch, int image_height, int image_width, int crop_height, int crop_width, int depth,
+                                   float extrapolation_value, float *crops, const int64_t *crop_strides_host, void *stream);
+int mdt_crop_and_resize_2d_backward(const float *grads, const int64_t *grad_strides_host, const float *boxes, const int *box_ind, int num_boxes,
+                                    int batch, int image_height, int image_width, int crop_height, int crop_width, int depth,
+                                    float *grads_image, const int64_t *img_strides_host, int zero_init, int64_t image_numel, void *stream);
+
+/* ------------------------------------------------------------ anchor <-> GT matching --------------------------------------------------------
+ * replaces: utils/model_utils.py:505-619 gt_anchor_matching (+ compute_overlaps :83-110, compute_iou_{2D,3D} :35-79), which runs in numpy f64 on the host.
+ * anchors [A, 2*dim] f64, gt_boxes [G, 2*dim] f64, gt_class_ids [G] int32 (NULL => all 1, the RPN case of mrcnn.py:894).
+ * Outputs (device):
+ *   matches   [A] int32   : -1 negative / 0 neutral / class id positive — state BEFORE the random sub-sampling of model_utils.py:566-571
+ *   iou_argmax[A] int32   : row argmax (first index on ties, numpy semantics) — needed by the caller for delta targets
+ *   n_pos     [1] int32   : number of positive anchors
+ * neg_iou_thresh is 0.01 (3D) / 0.1 (2D) in the reference (:549-552); pos_iou_thresh = cf.anchor_matching_iou.
+ * workspace: mdt_anchor_match_workspace_bytes(G).
+ */
+size_t mdt_anchor_match_workspace_bytes(int num_gt);
+int mdt_anchor_match(int dim, const double *anchors, int num_anchors, const double *gt_boxes, const int *gt_class_ids, int num_gt,
+                     double neg_iou_thresh, double pos_iou_thresh, void *workspace, size_t workspace_bytes, int *matches, int *iou_argmax,
+                     int *n_pos, void *stream);
+/* delta targets for up to max_targets positive anchors in ascending anchor order (model_utils.py:573-617): out [max_targets, 2*dim] f64, zero padded.
+ * pos_ids [n_pos] int32 ascending anchor indices (after any sub-sampling done by the caller). std_dev [2*dim] f64 (host). */
+int mdt_anchor_delta_targets(int dim, const double *anchors, const double *gt_boxes, const int *iou_argmax, const int *pos_ids, int n_pos,
+                             int max_targets, const double *std_dev_host, double *targets_out, void *stream);
+
+/* ------------------------------------------------------------------ conv3d ----------------------------------------------------------------
+ * replaces: the nn.Conv3d (+bias, +ReLU) built by utils/model_utils.py:739-781 NDConvGenerator and consumed by models/backbone.py:27-206.
+ * Layout: activations NDHWC ("channels_last_3d"): x [N, D, H, W, C] f32 contiguous, where (D,H,W) are the reference's (y,x,z) axes.
+ *         weights in the reference's parameter layout [Cout, Cin, kd, kh, kw] f32 contiguous (state-dict compatible).
+ * Descriptor struct keeps the signature stable across kernels.
+ */
+typedef struct mdt_conv3d_desc {
+    int n, d, h, w;          /* input batch and spatial extent */
+    int cin, cout;
+    int kd, kh, kw;
+    int sd, sh, sw;          /* strides */
+    int pd, ph, pw;          /* zero padding */
+    int relu;                /* fuse ReLU into the fprop epilogue */
+    int precision;           /* 0 = fp32-faithful (3-pass split-bf16 on tcgen05, or fp32 SIMT); 1 = single-pass bf16 (throughput mode) */
+    int algo;                /* 0 = auto, 1 = force SIMT direct kernels, 2 = force tcgen05 implicit GEMM (error if shape unsupported) */
+} mdt_conv3d_desc;
+
+size_t mdt_conv3d_workspace_bytes(const mdt_conv3d_desc *desc_host, int pass /*0 fprop,1 dgrad,2 wgrad*/);
+/* y = relu?(conv(x, w) + bias); bias may be NULL; residual (same shape as y, may be NULL) is added before the ReLU */
+int mdt_conv3d_fprop(const mdt_conv3d_desc *desc_host, const float *x, const float *w, const float *bias, const float *residual, float *y,
+                     void *workspace, size_t workspace_bytes, void *stream);
+/* dx = conv_transpose(dy, w) */
+int mdt_conv3d_dgrad(const mdt_conv3d_desc *desc_host, const float *dy, const float *w, float *dx, void *workspace, size_t workspace_bytes,
+                     void *stream);
+/* dw = x (*) dy ; db = sum(dy) (db may be NULL) */
+int mdt_conv3d_wgrad(const mdt_conv3d_desc *desc_host, const float *x, const float *dy, float *dw, float *db, void *workspace,
+                     size_t workspace_bytes, void *stream);
+/* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
+int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
+/* number of kernel launches issued by this library since load (all entry points) — feeds bench.py's gpu_launches */
+unsigned long long mdt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MDT_B200_H */

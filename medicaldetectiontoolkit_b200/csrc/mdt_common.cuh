@@ -1,0 +1,37 @@
+// Shared helpers for libmdt_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mdt_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libmdt_b200 is written for sm_100a only"
+#endif
+
+namespace mdt {
+
+extern unsigned long long g_launch_count;  // defined in capi.cu
+
+inline int launch_status() {
+    ++g_launch_count;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MDT_OK : (int)e;
+}
+
+inline int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+            sms = 148;
+    }
+    return sms;
+}
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace mdt

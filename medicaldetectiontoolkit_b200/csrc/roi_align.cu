@@ -1,0 +1,278 @@
+// RoIAlign (TF-style crop_and_resize, one tri-/bi-linear sample per output bin) forward + backward for sm_100a, 2D and 3D.
+//
+// Reference semantics followed (paths relative to the reference root):
+//   sampling coordinates  cuda_functions/roi_align_3D/roi_align/src/cuda/crop_and_resize_kernel.cu:52-106 ("fixed" half-bin-centred, clamped to the map)
+//   neighbours / lerp     :110-147   forward interpolation order (x, then y, then z)
+//   backward weights      :256-301   8 (2D: 4) scatter-adds into a zero-initialised image gradient
+//   bad box_ind           :43-47 + crop_and_resize_gpu.c:27: that crop is all zeros
+//   2D twin               cuda_functions/roi_align_2D/roi_align/src/cuda/crop_and_resize_kernel.cu:10-194
+//
+// B200 design: the reference runs one thread per output scalar over an NCDHW map, so the 8 gathers of a warp hit 8x32 different
+// sectors. Here the fast path works on channels-last maps (the layout the tcgen05 conv kernels produce): one thread owns one bin x 4
+// channels, so every corner read / gradient scatter of a warp is a run of consecutive 16-byte vectors (fully coalesced 128-bit
+// ld.global.nc / red.global.add.v4.f32). A stride-generic scalar kernel keeps the reference's NCDHW contract working with no copy.
+#include "mdt_common.cuh"
+
+namespace mdt {
+
+struct RoiGeom {
+    int num_boxes, batch, H, W, Z, ch, cw, cz, C;
+    int64_t is[5];  // image strides  (b, c, y, x, z) in elements
+    int64_t os[5];  // crop strides   (n, c, y, x, z) in elements
+};
+
+// sampling coordinate of output index `o` along one axis (crop extent `crop`, map extent `size`); expression form kept as in the
+// reference so that default nvcc contraction produces the same roundings
+__device__ __forceinline__ float sample_coord(float lo, float hi, int o, int crop, int size) {
+    const float scale = (crop > 1) ? (hi - lo) * (size) / (crop) : 0;
+    float t = (crop > 1) ? lo * (size) + o * scale + scale / 2 - 0.5 : 0.5 * (lo + hi) * (size);
+    if (t > size - 1) t = size - 1;
+    if (t < 0) t = 0;
+    return t;
+}
+
+struct Tap {
+    int lo, hi;
+    float lerp;
+};
+__device__ __forceinline__ Tap make_tap(float in) {
+    Tap t;
+    t.lo = (int)floorf(in);
+    t.hi = (int)ceilf(in);
+    t.lerp = in - t.lo;
+    return t;
+}
+
+template <int DIM>
+__device__ __forceinline__ bool bin_taps(const RoiGeom &g, const float *__restrict__ boxes, const int *__restrict__ box_ind, int n, int y, int x,
+                                         int z, Tap &ty, Tap &tx, Tap &tz, int &b_in) {
+    b_in = box_ind[n];
+    if (b_in < 0 || b_in >= g.batch) return false;
+    const float *bx = boxes + (size_t)n * (2 * DIM);
+    ty = make_tap(sample_coord(bx[0], bx[2], y, g.ch, g.H));
+    tx = make_tap(sample_coord(bx[1], bx[3], x, g.cw, g.W));
+    if (DIM == 3) tz = make_tap(sample_coord(bx[4], bx[5], z, g.cz, g.Z));
+    else { tz.lo = tz.hi = 0; tz.lerp = 0.f; }
+    return true;
+}
+
+// ---------------------------------------------------------------- generic strided scalar kernels ----------------------------------------------------------------
+// thread -> one output scalar. c_fastest selects the thread->element order so that consecutive lanes touch consecutive addresses of the
+// dominant stream (channels for channels-last maps, z for the reference's NCDHW maps).
+template <int DIM>
+__global__ void __launch_bounds__(256) roi_fwd_scalar(RoiGeom g, const float *__restrict__ image, const float *__restrict__ boxes,
+                                                     const int *__restrict__ box_ind, float *__restrict__ crops, int c_fastest, long long total) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        int c, z, x, y;
+        if (c_fastest) { c = r % g.C; r /= g.C; z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; }
+        else           { z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; c = r % g.C; r /= g.C; }
+        const int n = (int)r;
+        float *out = crops + n * g.os[0] + c * g.os[1] + y * g.os[2] + x * g.os[3] + z * g.os[4];
+        Tap ty, tx, tz; int b;
+        if (!bin_taps<DIM>(g, boxes, box_ind, n, y, x, z, ty, tx, tz, b)) { *out = 0.f; continue; }
+        const float *p = image + b * g.is[0] + c * g.is[1];
+        float v[2];
+#pragma unroll
+        for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
+            const int64_t oz = (DIM == 3) ? (kz ? tz.hi : tz.lo) * g.is[4] : 0;
+            const float tl = __ldg(p + ty.lo * g.is[2] + tx.lo * g.is[3] + oz), tr = __ldg(p + ty.lo * g.is[2] + tx.hi * g.is[3] + oz);
+            const float bl = __ldg(p + ty.hi * g.is[2] + tx.lo * g.is[3] + oz), br = __ldg(p + ty.hi * g.is[2] + tx.hi * g.is[3] + oz);
+            const float top = tl + (tr - tl) * tx.lerp, bot = bl + (br - bl) * tx.lerp;
+            v[kz] = top + (bot - top) * ty.lerp;
+        }
+        *out = (DIM == 3) ? v[0] + (v[1] - v[0]) * tz.lerp : v[0];
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) roi_bwd_scalar(RoiGeom g, const float *__restrict__ grads, const float *__restrict__ boxes,
+                                                     const int *__restrict__ box_ind, float *__restrict__ gimg, int c_fastest, long long total) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        int c, z, x, y;
+        if (c_fastest) { c = r % g.C; r /= g.C; z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; }
+        else           { z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; c = r % g.C; r /= g.C; }
+        const int n = (int)r;
+        Tap ty, tx, tz; int b;
+        if (!bin_taps<DIM>(g, boxes, box_ind, n, y, x, z, ty, tx, tz, b)) continue;
+        const float gv = grads[n * g.os[0] + c * g.os[1] + y * g.os[2] + x * g.os[3] + z * g.os[4]];
+        float *p = gimg + b * g.is[0] + c * g.is[1];
+#pragma unroll
+        for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
+            const float wz = (DIM == 3) ? (kz ? tz.lerp : 1 - tz.lerp) : 1.f;
+            const int64_t oz = (DIM == 3) ? (kz ? tz.hi : tz.lo) * g.is[4] : 0;
+#pragma unroll
+            for (int ky = 0; ky < 2; ++ky) {
+                const float wy = ky ? ty.lerp : 1 - ty.lerp;
+                const int64_t oy = (ky ? ty.hi : ty.lo) * g.is[2];
+#pragma unroll
+                for (int kx = 0; kx < 2; ++kx) {
+                    const float wx = kx ? tx.lerp : 1 - tx.lerp;
+                    // weight product order of the reference: x * z * y * grad
+                    const float w = (DIM == 3) ? wx * wz * wy * gv : wx * wy * gv;
+                    if (w != 0.f) atomicAdd(p + oy + (kx ? tx.hi : tx.lo) * g.is[3] + oz, w);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- channels-last float4 kernels ----------------------------------------------------------------
+// requires is[1] == 1, os[1] == 1, C % 4 == 0, all other strides % 4 == 0 and 16-byte aligned bases.
+template <int DIM>
+__global__ void __launch_bounds__(256) roi_fwd_cl4(RoiGeom g, const float *__restrict__ image, const float *__restrict__ boxes,
+                                                  const int *__restrict__ box_ind, float *__restrict__ crops, long long total) {
+    const int C4 = g.C >> 2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        const int c4 = r % C4; r /= C4;
+        const int z = r % g.cz; r /= g.cz;
+        const int x = r % g.cw; r /= g.cw;
+        const int y = r % g.ch; r /= g.ch;
+        const int n = (int)r;
+        float4 *out = reinterpret_cast<float4 *>(crops + n * g.os[0] + y * g.os[2] + x * g.os[3] + z * g.os[4]) + c4;
+        Tap ty, tx, tz; int b;
+        if (!bin_taps<DIM>(g, boxes, box_ind, n, y, x, z, ty, tx, tz, b)) { *out = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        const float *p = image + b * g.is[0] + 4 * c4;
+        float4 v[2];
+#pragma unroll
+        for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
+            const int64_t oz = (DIM == 3) ? (kz ? tz.hi : tz.lo) * g.is[4] : 0;
+            const float4 tl = __ldg(reinterpret_cast<const float4 *>(p + ty.lo * g.is[2] + tx.lo * g.is[3] + oz));
+            const float4 tr = __ldg(reinterpret_cast<const float4 *>(p + ty.lo * g.is[2] + tx.hi * g.is[3] + oz));
+            const float4 bl = __ldg(reinterpret_cast<const float4 *>(p + ty.hi * g.is[2] + tx.lo * g.is[3] + oz));
+            const float4 br = __ldg(reinterpret_cast<const float4 *>(p + ty.hi * g.is[2] + tx.hi * g.is[3] + oz));
+#define MDT_LERP2(f) { const float top = tl.f + (tr.f - tl.f) * tx.lerp, bot = bl.f + (br.f - bl.f) * tx.lerp; v[kz].f = top + (bot - top) * ty.lerp; }
+            MDT_LERP2(x) MDT_LERP2(y) MDT_LERP2(z) MDT_LERP2(w)
+#undef MDT_LERP2
+        }
+        float4 o = v[0];
+        if (DIM == 3) {
+            o.x = v[0].x + (v[1].x - v[0].x) * tz.lerp; o.y = v[0].y + (v[1].y - v[0].y) * tz.lerp;
+            o.z = v[0].z + (v[1].z - v[0].z) * tz.lerp; o.w = v[0].w + (v[1].w - v[0].w) * tz.lerp;
+        }
+        *out = o;
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) roi_bwd_cl4(RoiGeom g, const float *__restrict__ grads, const float *__restrict__ boxes,
+                                                  const int *__restrict__ box_ind, float *__restrict__ gimg, long long total) {
+    const int C4 = g.C >> 2;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long r = t;
+        const int c4 = r % C4; r /= C4;
+        const int z = r % g.cz; r /= g.cz;
+        const int x = r % g.cw; r /= g.cw;
+        const int y = r % g.ch; r /= g.ch;
+        const int n = (int)r;
+        Tap ty, tx, tz; int b;
+        if (!bin_taps<DIM>(g, boxes, box_ind, n, y, x, z, ty, tx, tz, b)) continue;
+        const float4 gv = __ldg(reinterpret_cast<const float4 *>(grads + n * g.os[0] + y * g.os[2] + x * g.os[3] + z * g.os[4]) + c4);
+        float *p = gimg + b * g.is[0] + 4 * c4;
+#pragma unroll
+        for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
+            const float wz = (DIM == 3) ? (kz ? tz.lerp : 1 - tz.lerp) : 1.f;
+            const int64_t oz = (DIM == 3) ? (kz ? tz.hi : tz.lo) * g.is[4] : 0;
+#pragma unroll
+            for (int ky = 0; ky < 2; ++ky) {
+                const float wy = ky ? ty.lerp : 1 - ty.lerp;
+                const int64_t oy = (ky ? ty.hi : ty.lo) * g.is[2];
+#pragma unroll
+                for (int kx = 0; kx < 2; ++kx) {
+                    const float wx = kx ? tx.lerp : 1 - tx.lerp;
+                    const float w = (DIM == 3) ? wx * wz * wy : wx * wy;
+                    if (w != 0.f)  // one 128-bit reduction (RED.E.ADD.F32x4) instead of four scalar atomics
+                        atomicAdd(reinterpret_cast<float4 *>(p + oy + (kx ? tx.hi : tx.lo) * g.is[3] + oz),
+                                  make_float4(w * gv.x, w * gv.y, w * gv.z, w * gv.w));
+                }
+            }
+        }
+    }
+}
+
+static bool cl4_ok(const RoiGeom &g, const void *img, const void *crop) {
+    if (g.C % 4 || g.is[1] != 1 || g.os[1] != 1) return false;
+    for (int k : {0, 2, 3, 4})
+        if (g.is[k] % 4 || g.os[k] % 4) return false;
+    return ((uintptr_t)img % 16 == 0) && ((uintptr_t)crop % 16 == 0);
+}
+
+static int grid_for(long long total, int block) {
+    long long need = (total + block - 1) / block;
+    long long cap = (long long)num_sms() * 32;  // 8 resident CTAs of 256 threads per SM x 4 waves; grid-stride covers the rest
+    return (int)(need < cap ? need : cap);
+}
+
+template <int DIM>
+static int roi_forward(const float *image, const int64_t *is, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W, int Z,
+                       int ch, int cw, int cz, int C, float *crops, const int64_t *os, cudaStream_t st) {
+    if (num_boxes < 0 || batch <= 0 || H <= 0 || W <= 0 || Z <= 0 || ch <= 0 || cw <= 0 || cz <= 0 || C <= 0 || !is || !os) return MDT_EINVAL;
+    if (num_boxes == 0) return MDT_OK;
+    if (!image || !boxes || !box_ind || !crops) return MDT_EINVAL;
+    RoiGeom g{num_boxes, batch, H, W, Z, ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = os[k]; }
+    const long long total = (long long)num_boxes * C * ch * cw * cz;
+    if (cl4_ok(g, image, crops)) {
+        roi_fwd_cl4<DIM><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
+    } else {
+        const int c_fastest = (g.is[1] == 1);
+        roi_fwd_scalar<DIM><<<grid_for(total, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, c_fastest, total);
+    }
+    return launch_status();
+}
+
+template <int DIM>
+static int roi_backward(const float *grads, const int64_t *gs, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W, int Z,
+                        int ch, int cw, int cz, int C, float *gimg, const int64_t *is, int zero_init, int64_t image_numel, cudaStream_t st) {
+    if (num_boxes < 0 || batch <= 0 || H <= 0 || W <= 0 || Z <= 0 || ch <= 0 || cw <= 0 || cz <= 0 || C <= 0 || !is || !gs || !gimg) return MDT_EINVAL;
+    if (zero_init) {
+        if (image_numel <= 0) return MDT_EINVAL;
+        cudaError_t e = cudaMemsetAsync(gimg, 0, (size_t)image_numel * sizeof(float), st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (num_boxes == 0) return MDT_OK;
+    if (!grads || !boxes || !box_ind) return MDT_EINVAL;
+    RoiGeom g{num_boxes, batch, H, W, Z, ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = gs[k]; }
+    const long long total = (long long)num_boxes * C * ch * cw * cz;
+    if (cl4_ok(g, gimg, grads)) {
+        roi_bwd_cl4<DIM><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
+    } else {
+        const int c_fastest = (g.is[1] == 1);
+        roi_bwd_scalar<DIM><<<grid_for(total, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, c_fastest, total);
+    }
+    return launch_status();
+}
+
+}  // namespace mdt
+
+extern "C" {
+
+int mdt_crop_and_resize_3d_forward(const float *image, const int64_t *is, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W,
+                                   int Z, int ch, int cw, int cz, int depth, float /*extrapolation_value*/, float *crops, const int64_t *os, void *stream) {
+    return mdt::roi_forward<3>(image, is, boxes, box_ind, num_boxes, batch, H, W, Z, ch, cw, cz, depth, crops, os, mdt::as_stream(stream));
+}
+int mdt_crop_and_resize_3d_backward(const float *grads, const int64_t *gs, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W,
+                                    int Z, int ch, int cw, int cz, int depth, float *gimg, const int64_t *is, int zero_init, int64_t image_numel,
+                                    void *stream) {
+    return mdt::roi_backward<3>(grads, gs, boxes, box_ind, num_boxes, batch, H, W, Z, ch, cw, cz, depth, gimg, is, zero_init, image_numel,
+                                mdt::as_stream(stream));
+}
+static void pad2d(const int64_t *s, int64_t *o) { o[0] = s ? s[0] : 0; o[1] = s ? s[1] : 0; o[2] = s ? s[2] : 0; o[3] = s ? s[3] : 0; o[4] = 0; }
+int mdt_crop_and_resize_2d_forward(const float *image, const int64_t *is, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W,
+                                   int ch, int cw, int depth, float /*extrapolation_value*/, float *crops, const int64_t *os, void *stream) {
+    if (!is || !os) return MDT_EINVAL;
+    int64_t i5[5], o5[5]; pad2d(is, i5); pad2d(os, o5);
+    return mdt::roi_forward<2>(image, i5, boxes, box_ind, num_boxes, batch, H, W, 1, ch, cw, 1, depth, crops, o5, mdt::as_stream(stream));
+}
+int mdt_crop_and_resize_2d_backward(const float *grads, const int64_t *gs, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W,
+                                    int ch, int cw, int depth, float *gimg, const int64_t *is, int zero_init, int64_t image_numel, void *stream) {
+    if (!is || !gs) return MDT_EINVAL;
+    int64_t i5[5], g5[5]; pad2d(is, i5); pad2d(gs, g5);
+    return mdt::roi_backward<2>(grads, g5, boxes, box_ind, num_boxes, batch, H, W, 1, ch, cw, 1, depth, gimg, i5, zero_init, image_numel,
+                                mdt::as_stream(stream));
+}
+
+}  // extern "C"

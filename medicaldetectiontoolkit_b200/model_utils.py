@@ -1,0 +1,235 @@
+"""Host-side mirror of the hot-path entry points of the reference's utils/model_utils.py, backed by libmdt_b200.so.
+
+Same names, argument meaning and return types as the reference so its model files can bind to them unchanged:
+  generate_pyramid_anchors   utils/model_utils.py:275-314 (+ generate_anchors :190-226, generate_anchors_3D :230-272)
+  gt_anchor_matching         utils/model_utils.py:505-619  -> device kernels (csrc/anchor_match.cu)
+  apply_box_deltas_{2D,3D}   :319-370, clip_boxes_{2D,3D} :376-398, clip_to_window :623-637, box_refinement :114-143
+  NDConvGenerator            :732-781  -> re-exported from .conv (tcgen05 conv3d modules)
+Anchor generation is init-time numpy (fp64, same operation order as the reference so the arrays are bit-identical); everything per
+step runs on the GPU.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+# ----------------------------------------------------------------------------------------------------------------- anchors (init time)
+def _anchor_shapes(scales_xy, scales_z, ratios):
+    """per-position anchor extents, ratio-major / scale-minor like np.meshgrid(scales, ratios).flatten() in the reference"""
+    s = np.asarray(scales_xy, dtype=np.float64)
+    r = np.asarray(ratios, dtype=np.float64)
+    sq = np.sqrt(np.repeat(r, len(s)))
+    s_t = np.tile(s, len(r))
+    heights = s_t / sq
+    widths = s_t * sq
+    depths = None
+    if scales_z is not None:
+        depths = np.tile(np.asarray(scales_z, dtype=np.float64), len(s_t) // len(scales_z))
+    return heights, widths, depths
+
+
+def generate_anchors(scales, ratios, shape, feature_stride, anchor_stride):
+    """2D anchors [n_pos * n_shapes, (y1, x1, y2, x2)] f64; positions y-major/x-minor, shapes fastest (model_utils.py:190-226)"""
+    h, w, _ = _anchor_shapes(scales, None, ratios)
+    cy = (np.arange(0, shape[0], anchor_stride) * feature_stride).astype(np.float64)
+    cx = (np.arange(0, shape[1], anchor_stride) * feature_stride).astype(np.float64)
+    centers = np.stack(np.meshgrid(cy, cx, indexing="ij"), axis=-1).reshape(-1, 1, 2)
+    sizes = np.stack([h, w], axis=-1).reshape(1, -1, 2)
+    lo = (centers - 0.5 * sizes).reshape(-1, 2)
+    hi = (centers + 0.5 * sizes).reshape(-1, 2)
+    return np.concatenate([lo, hi], axis=1)
+
+
+def generate_anchors_3D(scales_xy, scales_z, ratios, shape, feature_stride_xy, feature_stride_z, anchor_stride):
+    """3D anchors [n_pos * n_shapes, (y1, x1, y2, x2, z1, z2)] f64; positions (y, x, z) with z fastest (model_utils.py:230-272)"""
+    h, w, d = _anchor_shapes(scales_xy, scales_z, ratios)
+    cy = (np.arange(0, shape[0], anchor_stride) * feature_stride_xy).astype(np.float64)
+    cx = (np.arange(0, shape[1], anchor_stride) * feature_stride_xy).astype(np.float64)
+    cz = (np.arange(0, shape[2], anchor_stride) * feature_stride_z).astype(np.float64)
+    centers = np.stack(np.meshgrid(cy, cx, cz, indexing="ij"), axis=-1).reshape(-1, 1, 3)
+    sizes = np.stack([h, w, d], axis=-1).reshape(1, -1, 3)
+    lo = (centers - 0.5 * sizes).reshape(-1, 3)
+    hi = (centers + 0.5 * sizes).reshape(-1, 3)
+    return np.stack([lo[:, 0], lo[:, 1], hi[:, 0], hi[:, 1], lo[:, 2], hi[:, 2]], axis=1)
+
+
+def generate_pyramid_anchors(logger, cf):
+    """all pyramid levels concatenated, level order = cf.pyramid_levels (model_utils.py:275-314)"""
+    out = []
+    for level in cf.pyramid_levels:
+        fshape = cf.backbone_shapes[level]
+        if len(fshape) == 2:
+            out.append(generate_anchors(cf.rpn_anchor_scales['xy'][level], cf.rpn_anchor_ratios, fshape,
+                                        cf.backbone_strides['xy'][level], cf.rpn_anchor_stride))
+        else:
+            out.append(generate_anchors_3D(cf.rpn_anchor_scales['xy'][level], cf.rpn_anchor_scales['z'][level], cf.rpn_anchor_ratios, fshape,
+                                           cf.backbone_strides['xy'][level], cf.backbone_strides['z'][level], cf.rpn_anchor_stride))
+        if logger is not None:
+            logger.info("level {}: built anchors {}".format(level, out[-1].shape))
+    return np.concatenate(out, axis=0)
+
+
+# ----------------------------------------------------------------------------------------------------------------- matching (per step, device)
+_anchor_cache = {}
+
+
+def _device_anchors(anchors, device):
+    """fp64 device copy of the (constant) anchor array; cached so the 65 MB upload at A = 1.35 M happens once, not per step"""
+    if torch.is_tensor(anchors):
+        if anchors.dtype != torch.float64 or not anchors.is_cuda:
+            raise L.MdtError("device anchors must be a float64 CUDA tensor")
+        return anchors.contiguous()
+    key = (anchors.__array_interface__['data'][0], anchors.shape, str(device))
+    hit = _anchor_cache.get(key)
+    if hit is None or hit[1] is not anchors:
+        t = torch.from_numpy(np.ascontiguousarray(anchors, dtype=np.float64)).to(device)
+        _anchor_cache.clear()
+        _anchor_cache[key] = (t, anchors)
+        return t
+    return hit[0]
+
+
+def anchor_match_device(anchors_dev, gt_boxes_dev, gt_class_ids_dev, dim, neg_iou_thresh, pos_iou_thresh):
+    """Raw device call: labels BEFORE sub-sampling.  Returns (matches[A] i32, iou_argmax[A] i32, n_pos[1] i32), all CUDA, no sync."""
+    lib = L.load()
+    A = anchors_dev.shape[0]
+    G = 0 if gt_boxes_dev is None else gt_boxes_dev.shape[0]
+    dev = anchors_dev.device
+    matches = torch.empty(A, dtype=torch.int32, device=dev)
+    argmax = torch.empty(A, dtype=torch.int32, device=dev)
+    n_pos = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.mdt_anchor_match_workspace_bytes(G)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        L.check(lib.mdt_anchor_match(dim, L.ptr(anchors_dev), A, L.ptr(gt_boxes_dev), L.ptr(gt_class_ids_dev), G, float(neg_iou_thresh),
+                                     float(pos_iou_thresh), L.ptr(ws), ws_bytes, L.ptr(matches), L.ptr(argmax), L.ptr(n_pos), L.stream_ptr()))
+    return matches, argmax, n_pos
+
+
+def anchor_delta_targets_device(anchors_dev, gt_boxes_dev, argmax, pos_ids, n_pos, max_targets, std_dev, dim):
+    lib = L.load()
+    out = torch.empty((max_targets, 2 * dim), dtype=torch.float64, device=anchors_dev.device)
+    sd = (ctypes.c_double * (2 * dim))(*[float(v) for v in std_dev])
+    with torch.cuda.device(anchors_dev.device):
+        L.check(lib.mdt_anchor_delta_targets(dim, L.ptr(anchors_dev), L.ptr(gt_boxes_dev), L.ptr(argmax), L.ptr(pos_ids), int(n_pos),
+                                             int(max_targets), sd, L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids=None, device=None, rng=None):
+    """Device-resident twin of gt_anchor_matching: same semantics, returns CUDA tensors (matches int32 [A], targets float64 [T, 2*dim]).
+
+    rng: object with .choice(ids, extra, replace=False) used for the positive sub-sampling of model_utils.py:566-571; defaults to the
+    numpy global RNG so that a seeded run reproduces the reference's stream exactly.
+    """
+    dim = cf.dim
+    if device is None:
+        device = anchors.device if torch.is_tensor(anchors) else torch.device("cuda", torch.cuda.current_device())
+    a_dev = _device_anchors(anchors, device)
+    A = a_dev.shape[0]
+    T = cf.rpn_train_anchors_per_image
+    if gt_boxes is None or len(gt_boxes) == 0:
+        # model_utils.py:525-527 (gt_boxes is None): all negative, zero targets
+        return (torch.full((A,), -1, dtype=torch.int32, device=device), torch.zeros((T, 2 * dim), dtype=torch.float64, device=device))
+    g_dev = torch.as_tensor(np.asarray(gt_boxes, dtype=np.float64)).reshape(-1, 2 * dim).to(device) if not torch.is_tensor(gt_boxes) \
+        else gt_boxes.to(device=device, dtype=torch.float64).contiguous()
+    c_dev = None
+    if gt_class_ids is not None:
+        c_dev = torch.as_tensor(np.asarray(gt_class_ids).astype(np.int32)).to(device) if not torch.is_tensor(gt_class_ids) \
+            else gt_class_ids.to(device=device, dtype=torch.int32).contiguous()
+    neg_t = 0.1 if dim == 2 else 0.01  # model_utils.py:549-552
+    matches, argmax, n_pos = anchor_match_device(a_dev, g_dev, c_dev, dim, neg_t, cf.anchor_matching_iou)
+    pos_ids = torch.nonzero(matches > 0).squeeze(1)  # ascending, like np.where; sizes the result -> one host sync
+    extra = pos_ids.numel() - (T // 2)
+    if extra > 0:
+        chooser = rng if rng is not None else np.random
+        drop = chooser.choice(pos_ids.cpu().numpy(), extra, replace=False)
+        matches[torch.as_tensor(drop, device=device, dtype=torch.long)] = 0
+        pos_ids = torch.nonzero(matches > 0).squeeze(1)
+    targets = anchor_delta_targets_device(a_dev, g_dev, argmax, pos_ids.int().contiguous(), pos_ids.numel(), T, cf.rpn_bbox_std_dev, dim)
+    return matches, targets
+
+
+def gt_anchor_matching(cf, anchors, gt_boxes, gt_class_ids=None):
+    """Drop-in for utils/model_utils.py:505-619: numpy in, numpy out (anchor_class_matches int32 [A], anchor_delta_targets f64 [T, 2*dim]);
+    the IoU matrix, arg-maxes and labelling run on the GPU in fp64 with numpy's exact operation order."""
+    if gt_boxes is None:
+        # the reference returns an int64 array here (np.full without dtype, :526)
+        return np.full((anchors.shape[0],), -1), np.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim))
+    m, t = gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids)
+    return m.cpu().numpy(), t.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------------------------------------------- box coding (torch, device)
+def _split(boxes):
+    return [boxes[:, i] for i in range(boxes.shape[1])]
+
+
+def apply_box_deltas_2D(boxes, deltas):
+    """boxes [N,(y1,x1,y2,x2)], deltas [N,(dy,dx,log dh,log dw)] -> refined boxes (model_utils.py:319-340)"""
+    h = boxes[:, 2] - boxes[:, 0]
+    w = boxes[:, 3] - boxes[:, 1]
+    cy = boxes[:, 0] + 0.5 * h + deltas[:, 0] * h
+    cx = boxes[:, 1] + 0.5 * w + deltas[:, 1] * w
+    h = h * torch.exp(deltas[:, 2])
+    w = w * torch.exp(deltas[:, 3])
+    y1 = cy - 0.5 * h
+    x1 = cx - 0.5 * w
+    return torch.stack([y1, x1, y1 + h, x1 + w], dim=1)
+
+
+def apply_box_deltas_3D(boxes, deltas):
+    """boxes [N,(y1,x1,y2,x2,z1,z2)], deltas [N,(dy,dx,dz,log dh,log dw,log dd)] (model_utils.py:343-370)"""
+    h = boxes[:, 2] - boxes[:, 0]
+    w = boxes[:, 3] - boxes[:, 1]
+    d = boxes[:, 5] - boxes[:, 4]
+    cy = boxes[:, 0] + 0.5 * h + deltas[:, 0] * h
+    cx = boxes[:, 1] + 0.5 * w + deltas[:, 1] * w
+    cz = boxes[:, 4] + 0.5 * d + deltas[:, 2] * d
+    h = h * torch.exp(deltas[:, 3])
+    w = w * torch.exp(deltas[:, 4])
+    d = d * torch.exp(deltas[:, 5])
+    y1 = cy - 0.5 * h
+    x1 = cx - 0.5 * w
+    z1 = cz - 0.5 * d
+    return torch.stack([y1, x1, y1 + h, x1 + w, z1, z1 + d], dim=1)
+
+
+def clip_boxes_2D(boxes, window):
+    lo = boxes.new_tensor([window[0], window[1], window[0], window[1]], dtype=boxes.dtype)
+    hi = boxes.new_tensor([window[2], window[3], window[2], window[3]], dtype=boxes.dtype)
+    return torch.min(torch.max(boxes, lo), hi)
+
+
+def clip_boxes_3D(boxes, window):
+    lo = boxes.new_tensor([window[0], window[1], window[0], window[1], window[4], window[4]], dtype=boxes.dtype)
+    hi = boxes.new_tensor([window[2], window[3], window[2], window[3], window[5], window[5]], dtype=boxes.dtype)
+    return torch.min(torch.max(boxes, lo), hi)
+
+
+def clip_to_window(window, boxes):
+    """(model_utils.py:623-637) — note the argument order (window first)"""
+    return clip_boxes_3D(boxes, window) if boxes.shape[1] > 5 else clip_boxes_2D(boxes, window)
+
+
+def box_refinement(box, gt_box):
+    """deltas that move `box` onto `gt_box` (model_utils.py:114-143)"""
+    dim = box.shape[1] // 2
+    cols = [(0, 2), (1, 3)] + ([(4, 5)] if dim == 3 else [])
+    shift, scale = [], []
+    for lo, hi in cols:
+        e = box[:, hi] - box[:, lo]
+        ge = gt_box[:, hi] - gt_box[:, lo]
+        shift.append(((gt_box[:, lo] + 0.5 * ge) - (box[:, lo] + 0.5 * e)) / e)
+        scale.append(torch.log(ge / e))
+    return torch.stack(shift + scale, dim=1)
+
+
+def unique1d(tensor):
+    """sorted unique values (model_utils.py:645-654)"""
+    if tensor.numel() < 2:
+        return tensor
+    return torch.unique(tensor, sorted=True)

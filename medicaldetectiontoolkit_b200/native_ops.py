@@ -1,0 +1,191 @@
+"""Torch-facing wrappers of the native ops (NMS, RoIAlign) of libmdt_b200.so.
+
+Reference call surface mirrored (paths relative to the reference root):
+  cuda_functions/nms_3D/pth_nms.py:5-17                                 nms_gpu(dets, thresh) -> LongTensor keep (cuda)
+  cuda_functions/roi_align_3D/roi_align/crop_and_resize.py:10-69        CropAndResizeFunction / CropAndResize
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def nms_sorted(dets_sorted, thresh, dim):
+    """Greedy NMS on boxes ALREADY sorted by descending score, entirely on the device.
+
+    dets_sorted: [N, 2*dim+1] f32 cuda contiguous.  Returns (keep[N] int64 — first num entries valid, num[1] int32), both on the
+    device, no host synchronisation (the reduction of nms_cuda.c:33-61 runs in a kernel).
+    """
+    L.require_cuda(dets_sorted)
+    lib = L.load()
+    if dets_sorted.dtype != torch.float32 or dets_sorted.dim() != 2 or dets_sorted.shape[1] != 2 * dim + 1:
+        raise L.MdtError("nms: dets must be float32 [N, %d]" % (2 * dim + 1))
+    if not dets_sorted.is_contiguous():
+        raise L.MdtError("nms: boxes must be contiguous")  # same check as nms_cuda.c:19-20
+    n = dets_sorted.shape[0]
+    dev = dets_sorted.device
+    keep = torch.empty(n, dtype=torch.int64, device=dev)
+    num = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib.mdt_nms_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+    fn = lib.mdt_nms_3d if dim == 3 else lib.mdt_nms_2d
+    with torch.cuda.device(dev):
+        L.check(fn(L.ptr(dets_sorted), n, float(thresh), L.ptr(ws), ws_bytes, L.ptr(keep), L.ptr(num), L.stream_ptr()))
+    return keep, num
+
+
+def nms_gpu(dets, thresh, dim=None):
+    """Drop-in for pth_nms.nms_gpu: sort by the last column (descending), NMS, return indices into `dets` in descending-score order."""
+    if dim is None:
+        dim = (dets.shape[1] - 1) // 2
+    L.require_cuda(dets)
+    if dets.shape[0] == 0:
+        return torch.empty(0, dtype=torch.int64, device=dets.device)
+    scores = dets[:, -1]
+    order = scores.sort(0, descending=True)[1]
+    keep, num = nms_sorted(dets[order].contiguous().float(), thresh, dim)
+    return order[keep[: int(num.item())]].contiguous()  # the one sync the reference API shape requires (exact-length result)
+
+
+def nms_mask(dets_sorted, thresh, dim):
+    """Suppression bit-matrix [N, ceil(N/64)] (as int64 words), the contract of the reference's `_nms` (nms_kernel.h:11-12)."""
+    L.require_cuda(dets_sorted)
+    lib = L.load()
+    n = dets_sorted.shape[0]
+    cb = (n + 63) // 64
+    mask = torch.empty((n, cb), dtype=torch.int64, device=dets_sorted.device)
+    fn = lib.mdt_nms_mask_3d if dim == 3 else lib.mdt_nms_mask_2d
+    with torch.cuda.device(dets_sorted.device):
+        L.check(fn(n, L.ptr(dets_sorted.contiguous()), L.ptr(mask), float(thresh), L.stream_ptr()))
+    return mask
+
+
+def _strides5(t, dim):
+    """element strides of a logical [N, C, (spatial...)] tensor; 2D tensors are [N, C, H, W]"""
+    return L.i64arr(list(t.stride()))
+
+
+class _CropAndResize(torch.autograd.Function):
+    """static autograd.Function behind the reference's legacy instance-style Function (crop_and_resize.py:10-51)"""
+
+    @staticmethod
+    def forward(ctx, image, boxes, box_ind, crop_size, channels_last_out):
+        L.require_cuda(image, boxes, box_ind)
+        lib = L.load()
+        dim = len(crop_size)
+        if image.dim() != dim + 2:
+            raise L.MdtError("crop_and_resize: image must be [B, C, %s]" % ("Y, X, Z" if dim == 3 else "Y, X"))
+        if image.dtype != torch.float32:
+            raise L.MdtError("crop_and_resize: image must be float32")
+        boxes = boxes.detach().contiguous().float()
+        box_ind = box_ind.detach().contiguous().int()
+        n = boxes.shape[0]
+        B, C = image.shape[0], image.shape[1]
+        sp = list(image.shape[2:])
+        out_shape = [n, C] + list(crop_size)
+        if channels_last_out and dim == 3:
+            crops = torch.empty(out_shape, dtype=torch.float32, device=image.device, memory_format=torch.channels_last_3d)
+        elif channels_last_out and dim == 2:
+            crops = torch.empty(out_shape, dtype=torch.float32, device=image.device, memory_format=torch.channels_last)
+        else:
+            crops = torch.empty(out_shape, dtype=torch.float32, device=image.device)
+        img = image.detach()
+        with torch.cuda.device(image.device):
+            if dim == 3:
+                L.check(lib.mdt_crop_and_resize_3d_forward(L.ptr(img), L.i64arr(img.stride()), L.ptr(boxes), L.ptr(box_ind), n, B, sp[0], sp[1], sp[2],
+                                                           crop_size[0], crop_size[1], crop_size[2], C, 0.0, L.ptr(crops),
+                                                           L.i64arr(crops.stride()), L.stream_ptr()))
+            else:
+                L.check(lib.mdt_crop_and_resize_2d_forward(L.ptr(img), L.i64arr(img.stride()), L.ptr(boxes), L.ptr(box_ind), n, B, sp[0], sp[1],
+                                                           crop_size[0], crop_size[1], C, 0.0, L.ptr(crops), L.i64arr(crops.stride()),
+                                                           L.stream_ptr()))
+        ctx.save_for_backward(boxes, box_ind)
+        ctx.im_size = tuple(image.shape)
+        ctx.im_strides = tuple(image.stride())
+        ctx.crop_size = tuple(crop_size)
+        return crops
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        boxes, box_ind = ctx.saved_tensors
+        lib = L.load()
+        dim = len(ctx.crop_size)
+        B, C = ctx.im_size[0], ctx.im_size[1]
+        sp = ctx.im_size[2:]
+        # gradient gets the memory layout of the forward image (dense tensors only)
+        grad_image = torch.empty_strided(ctx.im_size, ctx.im_strides, dtype=torch.float32, device=grad_out.device)
+        dense = grad_image.numel() == _storage_extent(ctx.im_size, ctx.im_strides)
+        if not dense:
+            grad_image = torch.empty(ctx.im_size, dtype=torch.float32, device=grad_out.device)
+        g = grad_out.detach().float()
+        if not (g.is_contiguous() or g.is_contiguous(memory_format=torch.channels_last_3d if dim == 3 else torch.channels_last)):
+            g = g.contiguous()
+        n = boxes.shape[0]
+        with torch.cuda.device(grad_out.device):
+            if dim == 3:
+                L.check(lib.mdt_crop_and_resize_3d_backward(L.ptr(g), L.i64arr(g.stride()), L.ptr(boxes), L.ptr(box_ind), n, B, sp[0], sp[1], sp[2],
+                                                            ctx.crop_size[0], ctx.crop_size[1], ctx.crop_size[2], C, L.ptr(grad_image),
+                                                            L.i64arr(grad_image.stride()), 1, grad_image.numel(), L.stream_ptr()))
+            else:
+                L.check(lib.mdt_crop_and_resize_2d_backward(L.ptr(g), L.i64arr(g.stride()), L.ptr(boxes), L.ptr(box_ind), n, B, sp[0], sp[1],
+                                                            ctx.crop_size[0], ctx.crop_size[1], C, L.ptr(grad_image),
+                                                            L.i64arr(grad_image.stride()), 1, grad_image.numel(), L.stream_ptr()))
+        return grad_image, None, None, None, None
+
+
+def _storage_extent(size, stride):
+    ext = 1
+    for s, st in zip(size, stride):
+        if s == 0:
+            return 0
+        ext += (s - 1) * st
+    return ext
+
+
+class CropAndResizeFunction(object):
+    """Callable with the reference's construction/call shape:  CropAndResizeFunction(ch, cw[, cz], extrapolation_value)(image, boxes, box_ind).
+
+    2D form takes (crop_height, crop_width, extrapolation_value=0), 3D form (crop_height, crop_width, crop_zdepth, extrapolation_value=0)
+    (roi_align_2D/roi_align/crop_and_resize.py vs roi_align_3D/roi_align/crop_and_resize.py).  extrapolation_value is accepted and
+    unused, exactly as in the reference GPU kernel.  Gradient flows to `image` only (crop_and_resize.py:51).
+    Output layout follows the image: a channels-last image yields channels-last crops (logical shape is always [n, C, ch, cw(, cz)]).
+    """
+    dim = 3
+
+    def __init__(self, crop_height, crop_width, *rest):
+        if self.dim == 3:
+            if len(rest) < 1:
+                raise TypeError("3D CropAndResizeFunction needs crop_zdepth")
+            self.crop_size = (int(crop_height), int(crop_width), int(rest[0]))
+            self.extrapolation_value = rest[1] if len(rest) > 1 else 0
+        else:
+            self.crop_size = (int(crop_height), int(crop_width))
+            self.extrapolation_value = rest[0] if len(rest) > 0 else 0
+
+    def __call__(self, image, boxes, box_ind):
+        cl = image.stride(1) == 1 and image.shape[1] > 1
+        return _CropAndResize.apply(image, boxes, box_ind, self.crop_size, cl)
+
+    # legacy spelling used by some callers
+    forward = __call__
+
+
+class CropAndResizeFunction2D(CropAndResizeFunction):
+    dim = 2
+
+
+class CropAndResize(torch.nn.Module):
+    """nn.Module twin (crop_and_resize.py:54-69)"""
+    _fn = CropAndResizeFunction
+
+    def __init__(self, *args):
+        super().__init__()
+        self.fn = self._fn(*args)
+
+    def forward(self, image, boxes, box_ind):
+        return self.fn(image, boxes, box_ind)
+
+
+class CropAndResize2D(CropAndResize):
+    _fn = CropAndResizeFunction2D

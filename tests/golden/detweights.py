@@ -1,0 +1,26 @@
+"""Deterministic, name-keyed weights shared by make_golden.py (applied to the REFERENCE modules) and the tests (applied to ours):
+the fixtures then need not store 4 M parameters, and identical state-dict keys/shapes become part of what is tested."""
+import zlib
+
+import numpy as np
+import torch
+
+
+def fill_(module):
+    sd = module.state_dict()
+    weights = {k: v for k, v in sd.items()}
+    with torch.no_grad():
+        for name in sorted(weights):
+            p = weights[name]
+            wname = name[:-4] + "weight" if name.endswith("bias") else name
+            fan_in = int(np.prod(weights[wname].shape[1:]))
+            bound = 1.0 / np.sqrt(fan_in)
+            rs = np.random.RandomState(zlib.crc32(name.encode()) & 0x7fffffff)
+            p.copy_(torch.from_numpy(rs.uniform(-bound, bound, size=tuple(p.shape)).astype(np.float32)))
+    return module
+
+
+def subsample(t, limit=16384):
+    f = np.asarray(t).reshape(-1)
+    step = max(1, f.size // limit)
+    return f[::step].copy()
