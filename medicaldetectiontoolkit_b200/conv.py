@@ -1,0 +1,219 @@
+"""conv3d / conv2d modules and the NDConvGenerator factory on libmdt_b200's conv kernels.
+
+Reference surface mirrored: utils/model_utils.py:732-781 `NDConvGenerator(dim)(c_in, c_out, ks, pad=0, stride=1, norm=None, relu='relu')`
+returns nested nn.Sequential wrappers whose state-dict keys (`...0.weight`, `...0.bias`, bare `weight` when relu is None) and parameter
+shapes ([Cout, Cin, kd, kh, kw]) are kept, so reference checkpoints / initialisations load unchanged (SURVEY.md §5 checkpoint row).
+
+Activations are NDHWC in memory (torch.channels_last_3d; the logical shape stays [N, C, Y, X, Z] so the operator surface is unchanged).
+bias + ReLU (+ residual) are fused into the conv epilogue; the ReLU module that the reference appends stays in the Sequential as a
+parameter-free marker so the key structure is identical.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+_CL3 = torch.channels_last_3d
+
+# precision: 0 = fp32-faithful (3-pass split-bf16 on tcgen05 / fp32 SIMT), 1 = single-pass bf16 on tcgen05
+DEFAULT_PRECISION = 0
+# algo: 0 auto, 1 force SIMT, 2 force tcgen05
+DEFAULT_ALGO = 0
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """one grow-only scratch buffer per device/stream-less use: conv calls on a stream are ordered, so reuse is safe"""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _desc(x_shape, w_shape, stride, padding, relu, precision, algo):
+    n, cin, d, h, w = x_shape
+    cout, _, kd, kh, kw = w_shape
+    return L.Conv3dDesc(n, d, h, w, cin, cout, kd, kh, kw, stride[0], stride[1], stride[2], padding[0], padding[1], padding[2],
+                        int(bool(relu)), int(precision), int(algo))
+
+
+def _out_shape(x_shape, w_shape, stride, padding):
+    n, _, d, h, w = x_shape
+    cout, _, kd, kh, kw = w_shape
+    return (n, cout, (d + 2 * padding[0] - kd) // stride[0] + 1, (h + 2 * padding[1] - kh) // stride[1] + 1,
+            (w + 2 * padding[2] - kw) // stride[2] + 1)
+
+
+def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, precision=None, algo=None):
+    """y = relu?(conv3d(x, weight) + bias (+ residual)); x logical [N, C, D, H, W]; returns a channels_last_3d tensor. No autograd."""
+    lib = L.load()
+    L.require_cuda(x, weight, bias, residual)
+    precision = DEFAULT_PRECISION if precision is None else precision
+    algo = DEFAULT_ALGO if algo is None else algo
+    x = x.contiguous(memory_format=_CL3)
+    w = weight.contiguous()
+    y = torch.empty(_out_shape(x.shape, w.shape, stride, padding), dtype=torch.float32, device=x.device, memory_format=_CL3)
+    if residual is not None:
+        residual = residual.contiguous(memory_format=_CL3)
+    d = _desc(x.shape, w.shape, stride, padding, relu, precision, algo)
+    nbytes = lib.mdt_conv3d_workspace_bytes(d, 0)
+    ws = _workspace(nbytes, x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    return y
+
+
+def conv3d_dgrad(dy, weight, x_shape, stride, padding, precision=None, algo=None):
+    lib = L.load()
+    precision = DEFAULT_PRECISION if precision is None else precision
+    algo = DEFAULT_ALGO if algo is None else algo
+    dy = dy.contiguous(memory_format=_CL3)
+    w = weight.contiguous()
+    dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device, memory_format=_CL3)
+    d = _desc(x_shape, w.shape, stride, padding, False, precision, algo)
+    ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 1), dy.device)
+    with torch.cuda.device(dy.device):
+        L.check(lib.mdt_conv3d_dgrad(d, L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    return dx
+
+
+def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, algo=None):
+    lib = L.load()
+    precision = DEFAULT_PRECISION if precision is None else precision
+    algo = DEFAULT_ALGO if algo is None else algo
+    x = x.contiguous(memory_format=_CL3)
+    dy = dy.contiguous(memory_format=_CL3)
+    dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
+    db = torch.empty(w_shape[0], dtype=torch.float32, device=x.device) if want_bias else None
+    d = _desc(x.shape, w_shape, stride, padding, False, precision, algo)
+    ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 2), x.device)
+    with torch.cuda.device(x.device):
+        L.check(lib.mdt_conv3d_wgrad(d, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    return dw, db
+
+
+class _Conv3dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, stride, padding, relu, precision, algo):
+        y = conv3d_forward(x, weight, bias, stride, padding, relu, residual, precision, algo)
+        ctx.cfg = (stride, padding, relu, precision, algo, tuple(x.shape), bias is not None, residual is not None)
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        stride, padding, relu, precision, algo, x_shape, has_bias, has_res = ctx.cfg
+        gy = gy.contiguous(memory_format=_CL3)
+        if relu:
+            gy = torch.ops.aten.threshold_backward(gy, y, 0.0)  # ReLU mask (elementwise, HBM-bound)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = conv3d_dgrad(gy, weight, x_shape, stride, padding, precision, algo)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gw, gb = conv3d_wgrad(x, gy, tuple(weight.shape), stride, padding, has_bias, precision, algo)
+        gres = gy if (has_res and ctx.needs_input_grad[3]) else None
+        return gx, gw, gb, gres, None, None, None, None, None
+
+
+def _triple(v):
+    return tuple(int(i) for i in v) if isinstance(v, (tuple, list)) else (int(v),) * 3
+
+
+def _pair(v):
+    return tuple(int(i) for i in v) if isinstance(v, (tuple, list)) else (int(v),) * 2
+
+
+class Conv3d(nn.Module):
+    """nn.Conv3d-compatible module (same parameter names, shapes and default initialisation) running on libmdt_b200."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, fused_relu=False):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.fused_relu = fused_relu
+        self.precision = None
+        self.algo = None
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *self.kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # identical to torch.nn.modules.conv._ConvNd.reset_parameters, so a seeded build draws the same numbers as the reference's nn.Conv3d
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            fan_in = self.in_channels * self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+            bound = 1 / math.sqrt(fan_in) if fan_in > 0 else 0
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x, residual=None):
+        return _Conv3dFn.apply(x, self.weight, self.bias, residual, self.stride, self.padding, self.fused_relu, self.precision, self.algo)
+
+    def extra_repr(self):
+        return "{}, {}, kernel_size={}, stride={}, padding={}, fused_relu={}".format(
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.fused_relu)
+
+
+class Conv2d(nn.Module):
+    """nn.Conv2d-compatible module: runs as a depth-1 conv3d on the same kernels ([N, C, H, W] <-> [N, C, 1, H, W])"""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, bias=True, fused_relu=False):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding = _pair(kernel_size), _pair(stride), _pair(padding)
+        self.fused_relu = fused_relu
+        self.precision = None
+        self.algo = None
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *self.kernel_size))
+        self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        if self.bias is not None:
+            bound = 1 / math.sqrt(in_channels * self.kernel_size[0] * self.kernel_size[1])
+            nn.init.uniform_(self.bias, -bound, bound)
+
+    def forward(self, x, residual=None):
+        res = residual.unsqueeze(2) if residual is not None else None
+        y = _Conv3dFn.apply(x.unsqueeze(2), self.weight.unsqueeze(2), self.bias, res, (1,) + self.stride, (0,) + self.padding,
+                            self.fused_relu, self.precision, self.algo)
+        return y.squeeze(2)
+
+
+class FusedReLU(nn.Module):
+    """Parameter-free marker standing where the reference puts nn.ReLU(inplace=True): the ReLU already ran in the conv epilogue."""
+
+    def forward(self, x):
+        return x
+
+
+class NDConvGenerator(object):
+    """generic conv(+norm)(+relu) factory, 2D or 3D — same call shape and module nesting as utils/model_utils.py:732-781"""
+
+    def __init__(self, dim):
+        self.dim = dim
+
+    def __call__(self, c_in, c_out, ks, pad=0, stride=1, norm=None, relu='relu'):
+        fuse = (relu == 'relu') and norm is None
+        conv_cls = Conv2d if self.dim == 2 else Conv3d
+        conv = conv_cls(c_in, c_out, kernel_size=ks, padding=pad, stride=stride, fused_relu=fuse)
+        if norm is not None:
+            if norm == 'instance_norm':
+                norm_layer = nn.InstanceNorm2d(c_out) if self.dim == 2 else nn.InstanceNorm3d(c_out)
+            elif norm == 'batch_norm':
+                norm_layer = nn.BatchNorm2d(c_out) if self.dim == 2 else nn.BatchNorm3d(c_out)
+            else:
+                raise ValueError('norm type as specified in configs is not implemented... {}'.format(norm))
+            conv = nn.Sequential(conv, norm_layer)
+        if relu is not None:
+            if relu == 'relu':
+                relu_layer = FusedReLU() if fuse else nn.ReLU(inplace=True)
+            elif relu == 'leaky_relu':
+                relu_layer = nn.LeakyReLU(inplace=True)
+            else:
+                raise ValueError('relu type as specified in configs is not implemented...')
+            conv = nn.Sequential(conv, relu_layer)
+        return conv

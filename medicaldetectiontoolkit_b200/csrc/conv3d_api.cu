@@ -1,0 +1,63 @@
+// C-ABI of the conv3d path: algorithm selection (tcgen05 implicit GEMM vs fp32 SIMT) + workspace accounting.
+#include "conv3d_common.cuh"
+
+namespace mdt {
+static int pick_algo(const mdt_conv3d_desc *c, const ConvGeom &g, int pass) {
+    if (c->algo == 1) return 1;
+    const bool tc = conv_tc_supported(g, pass);
+    if (c->algo == 2) return tc ? 2 : 0;
+    return tc ? 2 : 1;
+}
+static size_t simt_ws(const ConvGeom &g, int pass) {
+    return pass == 2 ? 0 : sizeof(float) * (size_t)g.cout * g.cin * g.kd * g.kh * g.kw;
+}
+}  // namespace mdt
+
+extern "C" {
+
+int mdt_conv3d_algo(const mdt_conv3d_desc *c, int pass) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || pass < 0 || pass > 2) return MDT_EINVAL;
+    return mdt::pick_algo(c, g, pass);
+}
+
+size_t mdt_conv3d_workspace_bytes(const mdt_conv3d_desc *c, int pass) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || pass < 0 || pass > 2) return 0;
+    const int algo = mdt::pick_algo(c, g, pass);
+    size_t b = algo == 2 ? mdt::conv_tc_workspace_bytes(g, pass, c->precision) : mdt::simt_ws(g, pass);
+    return b + 256;
+}
+
+int mdt_conv3d_fprop(const mdt_conv3d_desc *c, const float *x, const float *w, const float *bias, const float *residual, float *y, void *ws,
+                     size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x || !w || !y) return MDT_EINVAL;
+    if (ws_bytes < mdt_conv3d_workspace_bytes(c, 0) || !ws) return MDT_EWORKSPACE;
+    const int algo = mdt::pick_algo(c, g, 0);
+    if (algo == 0) return MDT_EUNSUPPORTED;
+    if (algo == 2) return mdt::conv_tc_fprop(g, x, w, bias, residual, y, c->relu, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    return mdt::conv_simt_fprop(g, x, w, bias, residual, y, c->relu, ws, mdt::as_stream(stream));
+}
+
+int mdt_conv3d_dgrad(const mdt_conv3d_desc *c, const float *dy, const float *w, float *dx, void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !dy || !w || !dx) return MDT_EINVAL;
+    if (ws_bytes < mdt_conv3d_workspace_bytes(c, 1) || !ws) return MDT_EWORKSPACE;
+    const int algo = mdt::pick_algo(c, g, 1);
+    if (algo == 0) return MDT_EUNSUPPORTED;
+    if (algo == 2) return mdt::conv_tc_dgrad(g, dy, w, dx, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    return mdt::conv_simt_dgrad(g, dy, w, dx, ws, mdt::as_stream(stream));
+}
+
+int mdt_conv3d_wgrad(const mdt_conv3d_desc *c, const float *x, const float *dy, float *dw, float *db, void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x || !dy || !dw) return MDT_EINVAL;
+    if (ws_bytes < mdt_conv3d_workspace_bytes(c, 2)) return MDT_EWORKSPACE;
+    const int algo = mdt::pick_algo(c, g, 2);
+    if (algo == 0) return MDT_EUNSUPPORTED;
+    if (algo == 2) return mdt::conv_tc_wgrad(g, x, dy, dw, db, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    return mdt::conv_simt_wgrad(g, x, dy, dw, db, mdt::as_stream(stream));
+}
+
+}  // extern "C"

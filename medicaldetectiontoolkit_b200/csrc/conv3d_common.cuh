@@ -1,0 +1,41 @@
+// Shared conv3d geometry + internal entry points (SIMT and tcgen05 implementations).
+#pragma once
+#include "mdt_common.cuh"
+
+namespace mdt {
+
+struct ConvGeom {
+    int n, d, h, w, cin, cout;
+    int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+    int od, oh, ow;
+};
+
+inline bool make_geom(const mdt_conv3d_desc *c, ConvGeom &g) {
+    if (!c) return false;
+    g = ConvGeom{c->n, c->d, c->h, c->w, c->cin, c->cout, c->kd, c->kh, c->kw, c->sd, c->sh, c->sw, c->pd, c->ph, c->pw, 0, 0, 0};
+    if (g.n <= 0 || g.d <= 0 || g.h <= 0 || g.w <= 0 || g.cin <= 0 || g.cout <= 0 || g.kd <= 0 || g.kh <= 0 || g.kw <= 0 || g.sd <= 0 ||
+        g.sh <= 0 || g.sw <= 0 || g.pd < 0 || g.ph < 0 || g.pw < 0)
+        return false;
+    g.od = (g.d + 2 * g.pd - g.kd) / g.sd + 1;
+    g.oh = (g.h + 2 * g.ph - g.kh) / g.sh + 1;
+    g.ow = (g.w + 2 * g.pw - g.kw) / g.sw + 1;
+    return g.od > 0 && g.oh > 0 && g.ow > 0;
+}
+
+// SIMT (conv3d_simt.cu)
+int conv_simt_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, void *ws,
+                    cudaStream_t st);
+int conv_simt_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, void *ws, cudaStream_t st);
+int conv_simt_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, cudaStream_t st);
+int conv_bias_grad(const ConvGeom &g, const float *dy, float *db, cudaStream_t st);
+
+// tcgen05 (conv3d_tc.cu)
+bool conv_tc_supported(const ConvGeom &g, int pass);
+size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
+int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
+                  void *ws, size_t ws_bytes, cudaStream_t st);
+int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st);
+int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
+
+}  // namespace mdt
