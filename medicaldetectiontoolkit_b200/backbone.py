@@ -1,0 +1,167 @@
+"""FPN / ResNet backbone plugin on libmdt_b200 convs — same constructor, attribute names and output list as the reference's
+models/backbone.py:22-218 (`FPN(cf, conv, operate_stride1=False)`, `forward(x) -> [P0?, P2, P3, P4, P5, (P6)]`), so it can be named in
+`cf.backbone_path` (mrcnn.py:842-847, retina_unet.py:370-375) and loads the reference's state dicts key-for-key.
+
+B200 specifics: activations stay NDHWC (channels_last_3d) end to end; bias/ReLU run in the conv epilogues; the residual add + ReLU of a
+bottleneck block is fused into the epilogue of its third conv (backbone.py:195-206 does conv3 -> += residual -> ReLU as three passes).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .conv import Conv3d, Conv2d, _Conv3dFn
+
+_CL3 = torch.channels_last_3d
+
+
+def _to_cl(x):
+    return x.contiguous(memory_format=_CL3) if x.dim() == 5 else x.contiguous(memory_format=torch.channels_last)
+
+
+def _fused_residual_relu(conv_mod, x, residual):
+    """relu(conv(x) + bias + residual) in one kernel when conv_mod is a bare libmdt conv; generic fallback otherwise"""
+    if isinstance(conv_mod, Conv3d):
+        return _Conv3dFn.apply(x, conv_mod.weight, conv_mod.bias, _to_cl(residual), conv_mod.stride, conv_mod.padding, True, conv_mod.precision,
+                               conv_mod.algo)
+    if isinstance(conv_mod, Conv2d):
+        y = _Conv3dFn.apply(x.unsqueeze(2), conv_mod.weight.unsqueeze(2), conv_mod.bias, residual.unsqueeze(2), (1,) + conv_mod.stride,
+                            (0,) + conv_mod.padding, True, conv_mod.precision, conv_mod.algo)
+        return y.squeeze(2)
+    return None
+
+
+class ResBlock(nn.Module):
+    """bottleneck block: 1x1 (stride) -> 3x3 -> 1x1 (x4) + shortcut -> ReLU   (models/backbone.py:183-206)"""
+
+    def __init__(self, start_filts, planes, conv, stride=1, downsample=None, norm=None, relu='relu'):
+        super().__init__()
+        self.conv1 = conv(start_filts, planes, ks=1, stride=stride, norm=norm, relu=relu)
+        self.conv2 = conv(planes, planes, ks=3, pad=1, norm=norm, relu=relu)
+        self.conv3 = conv(planes, planes * 4, ks=1, norm=norm, relu=None)
+        self.relu = nn.ReLU(inplace=True) if relu == 'relu' else nn.LeakyReLU(inplace=True)
+        self.downsample = None
+        if downsample is not None:
+            self.downsample = conv(downsample[0], downsample[0] * downsample[1], ks=1, stride=downsample[2], norm=norm, relu=None)
+        self.stride = stride
+        self._fusable = (relu == 'relu') and norm is None
+
+    def forward(self, x):
+        shortcut = self.downsample(x) if self.downsample is not None else x
+        out = self.conv2(self.conv1(x))
+        if self._fusable:
+            fused = _fused_residual_relu(self.conv3, out, shortcut)
+            if fused is not None:
+                return fused
+        return self.relu(self.conv3(out) + shortcut)
+
+
+class Interpolate(nn.Module):
+    def __init__(self, scale_factor, mode):
+        super().__init__()
+        self.scale_factor = scale_factor
+        self.mode = mode
+
+    def forward(self, x):
+        return F.interpolate(x, scale_factor=self.scale_factor, mode=self.mode, align_corners=False)
+
+
+class FPN(nn.Module):
+    """Feature pyramid over a ResNet-50/101-style encoder; optional full-resolution decoder levels P1/P0 (`operate_stride1`)."""
+
+    def __init__(self, cf, conv, operate_stride1=False):
+        super().__init__()
+        sf = cf.start_filts
+        self.start_filts = sf
+        self.n_blocks = [3, 4, {"resnet50": 6, "resnet101": 23}[cf.res_architecture], 3]
+        self.block = ResBlock
+        self.block_expansion = 4
+        self.operate_stride1 = operate_stride1
+        self.sixth_pooling = cf.sixth_pooling
+        self.dim = conv.dim
+        three_d = conv.dim == 3
+        s221 = (2, 2, 1) if three_d else 2
+        blk = dict(conv=conv, norm=cf.norm, relu=cf.relu)
+
+        if operate_stride1:
+            self.C0 = nn.Sequential(conv(cf.n_channels, sf, ks=3, pad=1, norm=cf.norm, relu=cf.relu),
+                                    conv(sf, sf, ks=3, pad=1, norm=cf.norm, relu=cf.relu))
+            self.C1 = conv(sf, sf, ks=7, stride=s221, pad=3, norm=cf.norm, relu=cf.relu)
+        else:
+            self.C1 = conv(cf.n_channels, sf, ks=7, stride=s221, pad=3, norm=cf.norm, relu=cf.relu)
+
+        sfe = sf * self.block_expansion
+
+        def stage(c_in, planes, n, stride, first_downsample):
+            layers = [ResBlock(c_in, planes, stride=stride, downsample=first_downsample, **blk)]
+            layers += [ResBlock(planes * 4, planes, **blk) for _ in range(1, n)]
+            return layers
+
+        pool = nn.MaxPool3d(kernel_size=3, stride=(2, 2, 1), padding=1) if three_d else nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.C2 = nn.Sequential(pool, *stage(sf, sf, self.n_blocks[0], 1, (sf, self.block_expansion, 1)))
+        self.C3 = nn.Sequential(*stage(sfe, sf * 2, self.n_blocks[1], 2, (sfe, 2, 2)))
+        self.C4 = nn.Sequential(*stage(sfe * 2, sf * 4, self.n_blocks[2], 2, (sfe * 2, 2, 2)))
+        self.C5 = nn.Sequential(*stage(sfe * 4, sf * 8, self.n_blocks[3], 2, (sfe * 4, 2, 2)))
+        if self.sixth_pooling:
+            self.C6 = nn.Sequential(*stage(sfe * 8, sf * 16, self.n_blocks[3], 2, (sfe * 8, 2, 2)))
+
+        up = dict(scale_factor=(2, 2, 1), mode='trilinear') if three_d else dict(scale_factor=2, mode='bilinear')
+        self.P1_upsample = Interpolate(**up)
+        self.P2_upsample = Interpolate(**up)
+
+        oc = cf.end_filts
+        self.out_channels = oc
+        self.P5_conv1 = conv(sf * 32 + cf.n_latent_dims, oc, ks=1, stride=1, relu=None)
+        self.P4_conv1 = conv(sf * 16, oc, ks=1, stride=1, relu=None)
+        self.P3_conv1 = conv(sf * 8, oc, ks=1, stride=1, relu=None)
+        self.P2_conv1 = conv(sf * 4, oc, ks=1, stride=1, relu=None)
+        self.P1_conv1 = conv(sf, oc, ks=1, stride=1, relu=None)
+        if operate_stride1:
+            self.P0_conv1 = conv(sf, oc, ks=1, stride=1, relu=None)
+            self.P0_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        self.P1_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        self.P2_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        self.P3_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        self.P4_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        self.P5_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+        if self.sixth_pooling:
+            self.P6_conv1 = conv(sf * 64, oc, ks=1, stride=1, relu=None)
+            self.P6_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
+
+    @staticmethod
+    def _lateral(conv_mod, c, top):
+        """lateral 1x1 conv + nearest x2 upsampled coarser map, the add fused into the conv epilogue when possible"""
+        up = F.interpolate(top, scale_factor=2)
+        fused = None
+        if isinstance(conv_mod, Conv3d):
+            fused = _Conv3dFn.apply(c, conv_mod.weight, conv_mod.bias, _to_cl(up), conv_mod.stride, conv_mod.padding, False, conv_mod.precision,
+                                    conv_mod.algo)
+        return fused if fused is not None else conv_mod(c) + up
+
+    def forward(self, x):
+        """x [b, c, y, x, (z)] -> list of pyramid maps, finest first: [P0 (if operate_stride1), P2, P3, P4, P5, (P6)]"""
+        x = _to_cl(x)
+        c0 = self.C0(x) if self.operate_stride1 else x
+        c1 = self.C1(c0)
+        c2 = self.C2(c1)
+        c3 = self.C3(c2)
+        c4 = self.C4(c3)
+        c5 = self.C5(c4)
+        if self.sixth_pooling:
+            c6 = self.C6(c5)
+            p6_pre = self.P6_conv1(c6)
+            p5_pre = self._lateral(self.P5_conv1, c5, p6_pre)
+        else:
+            p5_pre = self.P5_conv1(c5)
+        p4_pre = self._lateral(self.P4_conv1, c4, p5_pre)
+        p3_pre = self._lateral(self.P3_conv1, c3, p4_pre)
+        p2_pre = self._lateral(self.P2_conv1, c2, p3_pre)
+
+        outs = [self.P2_conv2(p2_pre), self.P3_conv2(p3_pre), self.P4_conv2(p4_pre), self.P5_conv2(p5_pre)]
+        if self.sixth_pooling:
+            outs.append(self.P6_conv2(p6_pre))
+        if self.operate_stride1:
+            p1_pre = self.P1_conv1(c1) + self.P2_upsample(p2_pre)
+            p0_pre = self.P0_conv1(c0) + self.P1_upsample(p1_pre)
+            # P1_conv2 exists (and is in the state dict) but is unused, as in the reference (backbone.py:175)
+            outs = [self.P0_conv2(p0_pre)] + outs
+        return outs

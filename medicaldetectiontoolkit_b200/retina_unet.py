@@ -1,0 +1,336 @@
+"""Retina U-Net (one-stage detector + full-resolution segmentation head) on libmdt_b200 — the operator surface of the reference's
+models/retina_unet.py (`net(cf, logger)` with `train_forward(batch)`, `test_forward(batch)`, `forward(img)` and the same
+results_dict keys), re-designed so that a training step never leaves the GPU:
+
+  reference (file:line)                                         here
+  ------------------------------------------------------------  ------------------------------------------------------------------
+  Classifier / BBRegressor towers      retina_unet.py:40-119    same modules/keys, tcgen05 convs, logits stay channels-last (no permute copy)
+  numpy gt_anchor_matching per element retina_unet.py:416       fp64 device kernels (csrc/anchor_match.cu) through model_utils
+  compute_class_loss / shem            :126-164, mutils :674    fixed-shape top-k formulation, no nonzero()/host sync
+  refine_detections                    :194-271                 top-k instead of a 5.4 M-element sort; ONE batched multi-class NMS launch
+  nms_3D per (batch, class) + D2H mask pth_nms.py / nms_cuda.c  csrc/nms.cu bitmask + on-device reduction
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import model_utils as mutils
+from . import native_ops
+from .backbone import FPN
+from .conv import NDConvGenerator
+
+_CL3 = torch.channels_last_3d
+
+
+# ------------------------------------------------------------------------------------------------------------------ heads
+class _Tower(nn.Module):
+    """4 x (conv3 + ReLU) + conv3 -> [b, n_anchors, out_per_anchor]; shared across pyramid levels"""
+
+    def __init__(self, cf, conv, out_per_anchor):
+        super().__init__()
+        self.dim = conv.dim
+        self.out_per_anchor = out_per_anchor
+        n_in, n_feat, s = cf.end_filts, cf.n_rpn_features, cf.rpn_anchor_stride
+        self.conv_1 = conv(n_in, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
+        self.conv_2 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
+        self.conv_3 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
+        self.conv_4 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
+        self.conv_final = conv(n_feat, cf.n_anchors_per_pos * out_per_anchor, ks=3, stride=s, pad=1, relu=None)
+
+    def forward(self, x):
+        y = self.conv_final(self.conv_4(self.conv_3(self.conv_2(self.conv_1(x)))))
+        axes = (0, 2, 3, 1) if self.dim == 2 else (0, 2, 3, 4, 1)
+        # channels-last memory == the permuted layout the reference materialises with .permute().contiguous() (retina_unet.py:71-75)
+        y = y.permute(*axes).contiguous()
+        return [y.view(x.size(0), -1, self.out_per_anchor)]
+
+
+class Classifier(_Tower):
+    """class logits (b, n_anchors, n_classes)   (retina_unet.py:40-78)"""
+
+    def __init__(self, cf, conv):
+        super().__init__(cf, conv, cf.head_classes)
+        self.n_classes = cf.head_classes
+
+
+class BBRegressor(_Tower):
+    """box deltas (b, n_anchors, 2*dim)   (retina_unet.py:82-119)"""
+
+    def __init__(self, cf, conv):
+        super().__init__(cf, conv, conv.dim * 2)
+
+
+# ------------------------------------------------------------------------------------------------------------------ losses
+def compute_class_loss(anchor_matches, class_pred_logits, shem_poolsize=20, max_pos=None, generator=None):
+    """CE on positive anchors + CE on stochastically-hard-mined negatives (retina_unet.py:126-164, model_utils.py:674-691).
+
+    Fixed-shape, sync-free: positives (at most max_pos) and the SHEM pool (shem_poolsize * n_neg best-scoring negatives) are selected
+    with top-k + validity masks instead of nonzero().  Returns (loss, neg_anchor_ix) with neg_anchor_ix = indices INTO THE NEGATIVE
+    SUBSET like the reference (int64 CUDA tensor padded with -1).
+    """
+    A = anchor_matches.shape[0]
+    dev = class_pred_logits.device
+    k_pos = int(min(A, max_pos if max_pos is not None else 64))
+    pos_flag = (anchor_matches > 0)
+    n_pos = pos_flag.sum()
+    # first k_pos positive indices in ascending order (stable): key = index where positive, A otherwise
+    idx = torch.arange(A, device=dev)
+    pos_idx = torch.topk(torch.where(pos_flag, idx, idx.new_full((), A)), k_pos, largest=False, sorted=True)[0]
+    pos_valid = pos_idx < A
+    pos_idx_c = pos_idx.clamp_max(A - 1)
+    ce_pos = F.cross_entropy(class_pred_logits[pos_idx_c], anchor_matches[pos_idx_c].clamp_min(0).long(), reduction='none')
+    pos_loss = (ce_pos * pos_valid).sum() / pos_valid.sum().clamp_min(1)
+
+    neg_flag = (anchor_matches == -1)
+    n_neg_total = neg_flag.sum()
+    negative_count = n_pos.clamp_min(1)                                    # np.max((1, n_pos))
+    # hardest negatives by max foreground probability (softmax over ALL anchors is one streaming pass; masked afterwards)
+    probs = F.softmax(class_pred_logits.detach(), dim=1)
+    score = torch.where(neg_flag, probs[:, 1:].max(1)[0], probs.new_full((), -1.0))
+    k_pool = int(min(A, shem_poolsize * k_pos))
+    pool_score, pool_idx = torch.topk(score, k_pool, sorted=True)
+    pool_size = torch.minimum(shem_poolsize * negative_count, n_neg_total)   # model_utils.py:687
+    in_pool = (torch.arange(k_pool, device=dev) < pool_size) & (pool_score >= 0)
+    # sample `negative_count` of the pool without replacement: smallest random keys among pool members (== randperm(pool)[:n])
+    keys = torch.rand(k_pool, device=dev, generator=generator)
+    keys = torch.where(in_pool, keys, keys.new_full((), 2.0))
+    k_neg = int(min(k_pool, k_pos))
+    sel_key, sel = torch.topk(keys, k_neg, largest=False)
+    neg_valid = (torch.arange(k_neg, device=dev) < negative_count) & (sel_key < 1.5)
+    neg_idx = pool_idx[sel]
+    ce_neg = F.cross_entropy(class_pred_logits[neg_idx], torch.zeros(k_neg, dtype=torch.long, device=dev), reduction='none')
+    neg_loss = (ce_neg * neg_valid).sum() / neg_valid.sum().clamp_min(1)
+    # position of each sampled negative inside the negative subset (the reference indexes roi_logits_neg)
+    neg_rank = torch.cumsum(neg_flag.long(), 0) - 1
+    neg_ix = torch.where(neg_valid, neg_rank[neg_idx], neg_rank.new_full((), -1))
+    return (pos_loss + neg_loss) / 2, neg_ix
+
+
+def compute_bbox_loss(target_deltas, pred_deltas, anchor_matches, max_pos=None):
+    """smooth-L1 between the predicted deltas of the positive anchors (ascending anchor order) and their targets (retina_unet.py:167-187)"""
+    A = anchor_matches.shape[0]
+    dev = pred_deltas.device
+    k_pos = int(min(A, target_deltas.shape[0] if max_pos is None else max_pos))
+    idx = torch.arange(A, device=dev)
+    pos_idx = torch.topk(torch.where(anchor_matches > 0, idx, idx.new_full((), A)), k_pos, largest=False, sorted=True)[0]
+    valid = (pos_idx < A)
+    pred = pred_deltas[pos_idx.clamp_max(A - 1)]
+    l = F.smooth_l1_loss(pred, target_deltas[:k_pos].to(pred.dtype), reduction='none').sum(1)
+    n = valid.sum()
+    return (l * valid).sum() / (n.clamp_min(1) * pred.shape[1])   # mean over n_pos x 2*dim elements; 0 if no positive
+
+
+# ------------------------------------------------------------------------------------------------------------------ detections
+def refine_detections(anchors, probs, deltas, batch_ixs, cf):
+    """anchors (n_anchors, 2*dim); probs (b*n_anchors, n_classes); deltas (b*n_anchors, 2*dim); batch_ixs (b*n_anchors)
+    -> (n_det, (y1, x1, y2, x2, (z1), (z2), batch_ix, class_id, score)), at most model_max_instances_per_batch_element per element.
+
+    Same selection as retina_unet.py:194-271 (top pre_nms_limit foreground scores over the whole batch, decode, clip, round, NMS per
+    (batch element, class), top-k per element) but as ONE NMS launch: boxes of different (element, class) groups are translated apart
+    along y so they can never overlap; the coordinates are rounded pixels, so the IoUs inside a group are bit-identical.
+    """
+    dim = cf.dim
+    n_anchors = anchors.shape[0]
+    fg = probs[:, 1:]
+    n_fg = fg.shape[1]
+    k = int(min(cf.pre_nms_limit, fg.numel()))
+    scores, flat_ix = torch.topk(fg.reshape(-1), k, sorted=True)
+    row = torch.div(flat_ix, n_fg, rounding_mode='floor')                # torch-0.4 integer `/` (retina_unet.py:212)
+    class_ids = flat_ix - row * n_fg + 1
+    b_ix = batch_ixs[row]
+    pre_anchors = anchors[row % n_anchors]                                 # anchors.repeat(batch, 1)[row]
+    std_dev = torch.as_tensor(np.reshape(cf.rpn_bbox_std_dev, [1, dim * 2]), dtype=torch.float32, device=probs.device)
+    scale = torch.as_tensor(np.asarray(cf.scale), dtype=torch.float32, device=probs.device)
+    apply = mutils.apply_box_deltas_2D if dim == 2 else mutils.apply_box_deltas_3D
+    rois = apply(pre_anchors / scale, deltas[row] * std_dev) * scale
+    rois = torch.round(mutils.clip_to_window(cf.window, rois))
+
+    # batched multi-class NMS: translate each (batch, class) group to its own y band
+    n_groups_cls = n_fg + 1
+    band = float(max(cf.window[2], cf.window[3]) + 2)
+    offs = (b_ix * n_groups_cls + class_ids).to(rois.dtype) * band
+    shifted = rois.clone()
+    shifted[:, 0] += offs
+    shifted[:, 2] += offs
+    dets = torch.cat((shifted, scores.unsqueeze(1)), dim=1).contiguous()  # already sorted by descending score
+    keep_pad, num = native_ops.nms_sorted(dets, cf.detection_nms_threshold, dim)
+    kept = torch.zeros(k, dtype=torch.bool, device=probs.device)
+    pos = torch.arange(k, device=probs.device)
+    valid = pos < num.to(torch.long)
+    kept[keep_pad.clamp(0, k - 1)[valid]] = True
+    # top model_max_instances_per_batch_element per element, in score order
+    n_b = int(batch_ixs.max().item()) + 1 if batch_ixs.numel() else 1
+    onehot = (b_ix.unsqueeze(1) == torch.arange(n_b, device=probs.device).unsqueeze(0)) & kept.unsqueeze(1)
+    rank = torch.cumsum(onehot.long(), 0)
+    within = (rank * onehot).sum(1)
+    final = kept & (within <= cf.model_max_instances_per_batch_element)
+    sel = torch.nonzero(final).squeeze(1)                                  # variable-length result: the one sync of the forward
+    return torch.cat((rois[sel], b_ix[sel].unsqueeze(1).float(), class_ids[sel].unsqueeze(1).float(), scores[sel].unsqueeze(1)), dim=1)
+
+
+def get_results(cf, img_shape, detections, seg_logits, box_results_list=None):
+    """results_dict {'boxes': per-element lists of box dicts, 'seg_preds': uint8 label map} — retina_unet.py:275-333"""
+    det = detections.detach().cpu().numpy()
+    dim = cf.dim
+    if box_results_list is None:
+        box_results_list = [[] for _ in range(img_shape[0])]
+    for ix in range(img_shape[0]):
+        d = det[det[:, 2 * dim] == ix]
+        if d.shape[0] == 0:
+            continue
+        boxes = d[:, :2 * dim].astype(np.int32)
+        class_ids = d[:, 2 * dim + 1].astype(np.int32)
+        scores = d[:, 2 * dim + 2]
+        vol = (boxes[:, 2] - boxes[:, 0]) * (boxes[:, 3] - boxes[:, 1])
+        if dim == 3:
+            vol = vol * (boxes[:, 5] - boxes[:, 4])
+        ok = (vol > 0) & (scores >= cf.model_min_confidence)            # drop zero-volume boxes, keep confident ones
+        for b, s, c in zip(boxes[ok], scores[ok], class_ids[ok]):
+            box_results_list[ix].append({'box_coords': b, 'box_score': s, 'box_type': 'det', 'box_pred_class_id': c})
+    results = {'boxes': box_results_list}
+    if seg_logits is None:
+        results['seg_preds'] = np.zeros(img_shape)[:, 0][:, np.newaxis]
+    else:
+        results['seg_preds'] = seg_logits.detach().argmax(1, keepdim=True).to(torch.uint8).cpu().numpy()  # argmax(softmax) == argmax(logits)
+    return results
+
+
+# ------------------------------------------------------------------------------------------------------------------ net
+class net(nn.Module):
+    """Retina U-Net.  `operate_stride1`/seg head follow cf (set cf.operate_stride1 False and num_seg_classes 0 for plain RetinaNet)."""
+
+    has_seg_head = True
+
+    def __init__(self, cf, logger=None):
+        super().__init__()
+        self.cf = cf
+        self.logger = logger
+        self.build()
+        if getattr(cf, 'weight_init', None) is not None and logger is not None:
+            logger.info("weight_init {} requested: using the PyTorch default initialisation of the conv modules".format(cf.weight_init))
+
+    def build(self):
+        cf = self.cf
+        h, w = cf.patch_size[:2]
+        if h / 2 ** 5 != int(h / 2 ** 5) or w / 2 ** 5 != int(w / 2 ** 5):
+            raise Exception("Image size must be dividable by 2 at least 5 times to avoid fractions when downscaling and upscaling.")
+        conv = NDConvGenerator(cf.dim)
+        self.np_anchors = mutils.generate_pyramid_anchors(self.logger, cf)
+        self.register_buffer("anchors", torch.from_numpy(self.np_anchors).float(), persistent=False)
+        self.register_buffer("anchors_f64", torch.from_numpy(self.np_anchors).double(), persistent=False)
+        self.Fpn = FPN(cf, conv, operate_stride1=cf.operate_stride1)
+        self.Classifier = Classifier(cf, conv)
+        self.BBRegressor = BBRegressor(cf, conv)
+        if self.has_seg_head:
+            self.final_conv = conv(cf.end_filts, cf.num_seg_classes, ks=1, pad=0, norm=None, relu=None)
+
+    # -------------------------------------------------------------------------------------------------------------- forward
+    def forward(self, img):
+        """img (b, c, y, x, (z)) -> detections, class_logits (b, n_anchors, n_cls), bb_outputs (b, n_anchors, 2*dim), seg_logits"""
+        fpn_outs = self.Fpn(img)
+        if self.has_seg_head:
+            seg_logits = self.final_conv(fpn_outs[0])
+            first = 1
+        else:
+            seg_logits = None
+            first = 1 if self.cf.operate_stride1 else 0
+        fmaps = [fpn_outs[i + first] for i in self.cf.pyramid_levels]
+        class_logits = torch.cat([self.Classifier(p)[0] for p in fmaps], dim=1)
+        bb_outputs = torch.cat([self.BBRegressor(p)[0] for p in fmaps], dim=1)
+        b, a = class_logits.shape[0], class_logits.shape[1]
+        with torch.no_grad():
+            batch_ixs = torch.arange(b, device=img.device).unsqueeze(1).repeat(1, a).view(-1)
+            flat_softmax = F.softmax(class_logits.detach().view(-1, class_logits.shape[-1]), 1)
+            detections = refine_detections(self.anchors, flat_softmax, bb_outputs.detach().view(-1, bb_outputs.shape[-1]), batch_ixs, self.cf)
+        return detections, class_logits, bb_outputs, seg_logits
+
+    def _to_device(self, arr, dtype=torch.float32):
+        """host batch array -> device through pinned memory (non_blocking H2D)"""
+        dev = self.anchors.device
+        if torch.is_tensor(arr):
+            return arr.to(dev, dtype=dtype, non_blocking=True)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dev.type == 'cuda':
+            t = t.pin_memory()
+        return t.to(dev, non_blocking=True).to(dtype)
+
+    def train_forward(self, batch, **kwargs):
+        """batch: {'data', 'seg', 'bb_target', 'roi_labels', ...} numpy -> results_dict with 'torch_loss', 'boxes', 'seg_preds',
+        'monitor_values', 'logger_string' (retina_unet.py:381-456)."""
+        cf = self.cf
+        gt_class_ids = batch['roi_labels']
+        gt_boxes = batch['bb_target']
+        img = self._to_device(batch['data'])
+        n_b = img.shape[0]
+        box_results_list = [[] for _ in range(n_b)]
+        detections, class_logits, pred_deltas, seg_logits = self.forward(img)
+
+        max_pos = max(1, cf.rpn_train_anchors_per_image // 2)
+        batch_class_loss = img.new_zeros(1)
+        batch_bbox_loss = img.new_zeros(1)
+        monitor = []
+        for b in range(n_b):
+            if len(gt_boxes[b]) > 0:
+                for ix in range(len(gt_boxes[b])):
+                    box_results_list[b].append({'box_coords': batch['bb_target'][b][ix], 'box_label': batch['roi_labels'][b][ix], 'box_type': 'gt'})
+                match, target_deltas = mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], gt_class_ids[b])
+            else:
+                match = torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device)
+                target_deltas = torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device)
+            class_loss, neg_ix = compute_class_loss(match, class_logits[b], max_pos=max_pos)
+            bbox_loss = compute_bbox_loss(target_deltas, pred_deltas[b], match, max_pos=max_pos)
+            batch_class_loss = batch_class_loss + class_loss / n_b
+            batch_bbox_loss = batch_bbox_loss + bbox_loss / n_b
+            monitor.append((match, neg_ix))
+
+        loss = batch_class_loss + batch_bbox_loss
+        seg_dice = seg_ce = None
+        if self.has_seg_head:
+            seg = self._to_device(batch['seg'], dtype=torch.long)                     # (b, 1, y, x, (z))
+            seg_ohe = F.one_hot(seg[:, 0], cf.num_seg_classes).movedim(-1, 1).float()  # on-device one-hot (reference: numpy, retina_unet.py:395)
+            seg_dice = 1 - batch_dice(F.softmax(seg_logits, dim=1), seg_ohe)
+            seg_ce = F.cross_entropy(seg_logits, seg[:, 0])
+            loss = loss + (seg_dice + seg_ce) / 2
+
+        results_dict = get_results(cf, img.shape, detections, seg_logits, box_results_list)
+        if kwargs.get('monitor_anchors', True):
+            self._append_anchor_boxes(results_dict['boxes'], monitor, img.shape[2:])
+        results_dict['torch_loss'] = loss
+        vals = torch.stack([loss.detach().reshape(()), batch_class_loss.detach().reshape(()), batch_bbox_loss.detach().reshape(())]
+                           + ([seg_dice.detach().reshape(()), seg_ce.detach().reshape(())] if self.has_seg_head else [])).cpu().tolist()
+        results_dict['monitor_values'] = {'loss': vals[0], 'class_loss': vals[1]}
+        if self.has_seg_head:
+            results_dict['logger_string'] = "loss: {0:.2f}, class: {1:.2f}, bbox: {2:.2f}, seg dice: {3:.3f}, seg ce: {4:.3f}, mean pix. pr.: {5:.5f}" \
+                .format(vals[0], vals[1], vals[2], vals[3], vals[4], np.mean(results_dict['seg_preds']))
+        else:
+            results_dict['logger_string'] = "loss: {0:.2f}, class: {1:.2f}, bbox: {2:.2f}".format(vals[0], vals[1], vals[2])
+        return results_dict
+
+    def _append_anchor_boxes(self, boxes_list, monitor, spatial):
+        """positive / sampled-negative anchors for the monitoring plots (retina_unet.py:420-439)"""
+        hi = np.array([spatial[0], spatial[1], spatial[0], spatial[1]] + ([spatial[2], spatial[2]] if self.cf.dim == 3 else []))
+        for b, (match, neg_ix) in enumerate(monitor):
+            m = match.cpu().numpy()
+            pos = self.np_anchors[m > 0]
+            neg_all = np.where(m == -1)[0]
+            nix = neg_ix.cpu().numpy()
+            neg = self.np_anchors[neg_all[nix[nix >= 0]]] if neg_all.size else np.zeros((0, hi.size))
+            for p in np.clip(pos, 0, hi):
+                boxes_list[b].append({'box_coords': p, 'box_type': 'pos_anchor'})
+            for n in np.clip(neg, 0, hi):
+                boxes_list[b].append({'box_coords': n, 'box_type': 'neg_anchor'})
+
+    def test_forward(self, batch, **kwargs):
+        img = self._to_device(batch['data'])
+        with torch.no_grad():
+            detections, _, _, seg_logits = self.forward(img)
+        return get_results(self.cf, img.shape, detections, seg_logits)
+
+
+def batch_dice(pred, y, false_positive_weight=1.0, smooth=1e-6):
+    """soft dice over the batch pseudo-volume, foreground classes only (utils/model_utils.py:833-858)"""
+    axes = (0,) + tuple(range(2, pred.dim()))
+    intersect = (pred * y).sum(axes)
+    denom = (false_positive_weight * pred + y).sum(axes)
+    return torch.mean(((2 * intersect + smooth) / (denom + smooth))[1:])

@@ -74,7 +74,7 @@ def test_nms_dropin_api_and_mask():
         dets = torch.from_numpy(srt[perm]).to(DEV)
         got = fn(dets, 0.5)
         assert got.dtype == torch.int64 and got.is_cuda
-        want = perm[O.nms(srt, 0.5, dim)]  # indices into the unsorted input, descending score
+        want = np.argsort(perm)[O.nms(srt, 0.5, dim)]  # dets[i] = srt[perm[i]] -> index of sorted row j in dets is perm^-1[j]
         assert got.cpu().numpy().tolist() == want.tolist()
         assert fn(dets[:0], 0.5).numel() == 0
         m = NO.nms_mask(torch.from_numpy(srt[:777]).to(DEV), 0.5, dim).cpu().numpy().view(np.uint64)
