@@ -24,6 +24,9 @@ DEFAULT_ALGO = 0
 
 _ws_cache = {}
 
+# when a list, every conv kernel call appends a (start, end) CUDA-event pair recorded on the launching stream (bench.py roofline)
+EVENT_LOG = None
+
 
 def _workspace(nbytes, device):
     """one grow-only scratch buffer per device/stream-less use: conv calls on a stream are ordered, so reuse is safe"""
@@ -33,6 +36,21 @@ def _workspace(nbytes, device):
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
+
+
+def _ev_start():
+    if EVENT_LOG is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _ev_end(e0):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        EVENT_LOG.append((e0, e1))
 
 
 def _desc(x_shape, w_shape, stride, padding, relu, precision, algo):
@@ -64,7 +82,9 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
     nbytes = lib.mdt_conv3d_workspace_bytes(d, 0)
     ws = _workspace(nbytes, x.device)
     with torch.cuda.device(x.device):
+        ev = _ev_start()
         L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        _ev_end(ev)
     return y
 
 
@@ -78,7 +98,9 @@ def conv3d_dgrad(dy, weight, x_shape, stride, padding, precision=None, algo=None
     d = _desc(x_shape, w.shape, stride, padding, False, precision, algo)
     ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 1), dy.device)
     with torch.cuda.device(dy.device):
+        ev = _ev_start()
         L.check(lib.mdt_conv3d_dgrad(d, L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        _ev_end(ev)
     return dx
 
 
@@ -93,7 +115,9 @@ def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, alg
     d = _desc(x.shape, w_shape, stride, padding, False, precision, algo)
     ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 2), x.device)
     with torch.cuda.device(x.device):
+        ev = _ev_start()
         L.check(lib.mdt_conv3d_wgrad(d, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        _ev_end(ev)
     return dw, db
 
 

@@ -1,0 +1,31 @@
+"""Data-parallel gradient exchange: one process per GPU, ONE all-reduce per step over a flat fp32 gradient buffer.
+
+The reference has no multi-GPU code (exec.py:38 is single-device).  The path shards by patch with no data-path collective; the only
+exchange is the gradient sum.  All parameter .grad tensors are views into one contiguous buffer, so backward accumulates straight into
+the message and the averaged result is what the (fused) Adam reads — no flatten/unflatten copies.  Parameters that never receive a
+gradient (Fpn.P1_conv2.*, backbone.py:175) still sit in the buffer as zeros, which keeps the bucket list static across ranks.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGradAllReduce(object):
+    def __init__(self, module, world_size, group=None):
+        self.world = world_size
+        self.group = group
+        params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        self.flat = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.params = params
+
+    def zero_grad(self):
+        self.flat.zero_()
+
+    def all_reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / self.world)

@@ -1,0 +1,107 @@
+"""Backbone / model level parity (GPU).  The FPN mirror is compared with fixtures produced by the REFERENCE's models/backbone.py
+(stock nn.Conv3d, CPU fp32; tests/golden/make_golden.py) under identical, name-keyed deterministic weights — this also proves the
+state-dict keys and shapes are the reference's.  The Retina U-Net mirror is exercised end to end (train_forward + backward)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+import detweights  # noqa: E402
+
+from medicaldetectiontoolkit_b200 import conv as C  # noqa: E402
+from medicaldetectiontoolkit_b200.backbone import FPN  # noqa: E402
+from medicaldetectiontoolkit_b200.configs import make_cf, synthetic_batch  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("tag,op1", [("unet", True), ("mrcnn", False)])
+def test_fpn_vs_reference_fixture(golden_dir, tag, op1):
+    g = np.load(os.path.join(golden_dir, "backbone3d_%s.npz" % tag))
+    cf = make_cf('retina_unet' if op1 else 'mrcnn', 3, (32, 32, 16))
+    fpn = FPN(cf, C.NDConvGenerator(3), operate_stride1=op1)
+    keys = [k for k, _ in fpn.named_parameters()]
+    assert keys == list(g["keys"])                                             # same parameter names, same order
+    shapes = {k: tuple(v.shape) for k, v in fpn.state_dict().items()}
+    assert [str(shapes[k]) for k in keys] == list(g["key_shapes"])
+    detweights.fill_(fpn)
+    fpn = fpn.to(DEV)
+    x = torch.from_numpy(np.random.RandomState(3).rand(1, 1, 32, 32, 16).astype(np.float32)).to(DEV).requires_grad_(True)
+    outs = fpn(x)
+    for i, o in enumerate(outs):
+        assert tuple(o.shape) == tuple(g["outshape%d" % i])
+        assert _rel(detweights.subsample(o.detach().cpu().numpy()), g["out%d" % i]) < 1e-4, i
+    loss = sum((o * o).mean() for o in outs)
+    assert abs(loss.item() - float(g["loss"])) < 1e-4 * abs(float(g["loss"]))
+    loss.backward()
+    assert _rel(detweights.subsample(x.grad.cpu().numpy()), g["x_grad"]) < 1e-3
+    params = dict(fpn.named_parameters())
+    for k in g.files:
+        if k.startswith("grad__"):
+            assert _rel(detweights.subsample(params[k[6:]].grad.cpu().numpy()), g[k]) < 1e-3, k
+    assert sorted(k for k, p in params.items() if p.grad is None) == sorted(g["nograd"])   # P1_conv2.* never used (backbone.py:175)
+
+
+def test_retina_unet_train_step_small():
+    from medicaldetectiontoolkit_b200 import retina_unet
+    cf = make_cf('retina_unet', 3, (64, 64, 32))
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = retina_unet.net(cf, None).to(DEV)
+    batch = synthetic_batch(cf, 2, seed=1)
+    res = net.train_forward(batch)
+    assert set(['boxes', 'seg_preds', 'torch_loss', 'monitor_values', 'logger_string']) <= set(res)
+    assert res['seg_preds'].shape == (2, 1, 64, 64, 32) and res['seg_preds'].dtype == np.uint8
+    assert len(res['boxes']) == 2 and any(b['box_type'] == 'gt' for b in res['boxes'][0])
+    loss = res['torch_loss']
+    assert torch.isfinite(loss).all()
+    loss.backward()
+    grads = [(k, p.grad) for k, p in net.named_parameters()]
+    missing = sorted(k for k, g_ in grads if g_ is None)
+    assert missing == ['Fpn.P1_conv2.bias', 'Fpn.P1_conv2.weight']             # 154 of 156 parameters receive gradients
+    assert all(torch.isfinite(g_).all() for _, g_ in grads if g_ is not None)
+    n_params = sum(p.numel() for p in net.parameters())
+    assert n_params == 4_950_000 or abs(n_params - 4.95e6) < 0.05e6            # SURVEY: 4.95 M parameters
+    out = net.test_forward({'data': batch['data']})
+    assert 'boxes' in out and out['seg_preds'].shape == (2, 1, 64, 64, 32)
+
+
+def test_retina_losses_match_reference_formulas():
+    """fixed-shape loss formulation == the reference's nonzero()-based one (retina_unet.py:126-187) on a case with known sampling"""
+    from medicaldetectiontoolkit_b200.retina_unet import compute_bbox_loss, compute_class_loss
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    A = 5000
+    logits = torch.randn(A, 3, device=DEV)
+    match = torch.full((A,), -1, dtype=torch.int32, device=DEV)
+    match[torch.randperm(A, device=DEV)[:1500]] = 0
+    pos = torch.tensor([17, 901, 4000], device=DEV)
+    match[pos] = torch.tensor([1, 2, 1], dtype=torch.int32, device=DEV)
+    loss, neg_ix = compute_class_loss(match, logits, shem_poolsize=20, max_pos=3)
+    pos_loss = F.cross_entropy(logits[pos], match[pos].long())
+    neg_all = torch.nonzero(match == -1).squeeze(1)
+    picked = neg_all[neg_ix[neg_ix >= 0]]
+    assert picked.numel() == 3
+    probs = F.softmax(logits[neg_all], 1)[:, 1:].max(1)[0]
+    pool = neg_all[probs.sort(descending=True)[1][:60]]
+    assert set(picked.tolist()) <= set(pool.tolist())                          # sampled from the top shem_poolsize * n_neg pool
+    neg_loss = F.cross_entropy(logits[picked], torch.zeros(3, dtype=torch.long, device=DEV))
+    assert abs(loss.item() - ((pos_loss + neg_loss) / 2).item()) < 1e-5
+    deltas = torch.randn(A, 6, device=DEV)
+    tgt = torch.zeros(6, 6, dtype=torch.float64, device=DEV)
+    tgt[:3] = torch.randn(3, 6, dtype=torch.float64, device=DEV)
+    bl = compute_bbox_loss(tgt, deltas, match, max_pos=3)
+    want = F.smooth_l1_loss(deltas[pos], tgt[:3].float())
+    assert abs(bl.item() - want.item()) < 1e-6
+    none = torch.full((A,), -1, dtype=torch.int32, device=DEV)
+    assert compute_bbox_loss(tgt, deltas, none, max_pos=3).item() == 0.0
