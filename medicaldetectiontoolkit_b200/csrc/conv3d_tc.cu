@@ -1,9 +1,436 @@
-// tcgen05 implicit-GEMM conv3d — placeholder until the kernels land (returns "unsupported" so `auto` resolves to SIMT).
+// conv3d on the 5th-generation tensor cores (algo 2): implicit GEMM with TMA-staged operands, tcgen05.mma, TMEM accumulators.
+//
+// Replaces the cuDNN conv3d behind nn.Conv3d in the reference (utils/model_utils.py:762; models/backbone.py:27-206, heads in
+// models/retina_unet.py:40-119, models/mrcnn.py:40-169).
+//
+// GEMM view (fprop): rows M = output voxels, columns N = Cout, reduction K = taps x Cin.   dgrad: rows = input voxels, N = Cin, K = taps x Cout.
+//
+// fp32-faithful arithmetic on a bf16 tensor pipe ("split-bf16 x3"): every fp32 operand v is stored as two bf16 planes hi = rn(v),
+// lo = rn(v - hi) (|v - hi - lo| <= 2^-17 |v|); the kernel issues three MMAs per K step — A_hi*B_hi + A_hi*B_lo + A_lo*B_hi — into ONE fp32
+// TMEM accumulator, dropping only the lo*lo term (~2^-18).  precision = 1 issues the first MMA only (plain bf16 inputs).
+//
+// Data movement (the part that decides the roofline): a tile is 128 consecutive output voxels along the innermost spatial axis (the
+// reference's z).  For every (kd, kh) the TMA loads ONE halo line of 128 + kw - 1 voxels x a 16/32/64-channel chunk into a
+// hardware-swizzled shared-memory buffer, and the kw taps are issued as tcgen05.mma on row-SHIFTED windows of that buffer (the shared
+// memory matrix descriptor start address moves by kw rows; verified on B200 by tools/tc_probe, profiles/r01_tc_probe.txt).  Each input
+// element is therefore fetched kd*kh times per tile instead of kd*kh*kw times.  Zero padding = TMA out-of-bounds fill.  Tiles that are not
+// one full line (W < 128) use a box of BH lines x BW voxels per tap instead (generic mode).
+// Weights stream through their own ring as [Np x chunk] K-major tiles per tap.
+//
+// Warp roles (192 threads): warp 0 TMA producer (one lane), warp 1 TMEM allocator + MMA issuer (one lane), warps 2-5 epilogue
+// (TMEM -> registers -> bias / residual / ReLU -> global fp32 NDHWC).
 #include "conv3d_common.cuh"
+#include "tc_common.cuh"
+
 namespace mdt {
-bool conv_tc_supported(const ConvGeom &, int) { return false; }
-size_t conv_tc_workspace_bytes(const ConvGeom &, int, int) { return 0; }
-int conv_tc_fprop(const ConvGeom &, const float *, const float *, const float *, const float *, float *, int, int, void *, size_t, cudaStream_t) { return MDT_EUNSUPPORTED; }
-int conv_tc_dgrad(const ConvGeom &, const float *, const float *, float *, int, void *, size_t, cudaStream_t) { return MDT_EUNSUPPORTED; }
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------ operand preparation kernels
+// fp32 [rows, C] -> bf16 planes [planes][rows, Cp] (hi, lo), channels zero-padded to Cp (multiple of 16)
+__global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C,
+                                                        int Cp, int planes) {
+    const int groups = Cp / 8;  // 8 channels (16 bytes of bf16) per thread
+    const long long total = rows * groups;
+    const long long plane_stride = rows * Cp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / groups;
+        const int c0 = (int)(i % groups) * 8;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (c0 + k < C) ? __ldg(src + r * C + c0 + k) : 0.f;
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            hi[k] = __float2bfloat16_rn(v[k]);
+            lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
+        }
+        *reinterpret_cast<uint4 *>(dst + r * Cp + c0) = *reinterpret_cast<const uint4 *>(hi);
+        if (planes > 1) *reinterpret_cast<uint4 *>(dst + plane_stride + r * Cp + c0) = *reinterpret_cast<const uint4 *>(lo);
+    }
+}
+
+// weights [Cout, Cin, T] fp32 -> bf16 planes [planes][T][Nrows][Kp]  (K contiguous)
+//   mode 0 (fprop): Nrows = Cout (padded Np), K = Cin:  B[t][co][ci] = w[co][ci][t]
+//   mode 1 (dgrad): Nrows = Cin  (padded Np), K = Cout: B[t][ci][co] = w[co][ci][t]
+__global__ void __launch_bounds__(256) pack_weights_tc_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ dst, int cout, int cin, int T,
+                                                             int Np, int Kp, int planes, int mode) {
+    const long long total = (long long)T * Np * Kp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % Kp);
+        const int n = (int)((i / Kp) % Np);
+        const int t = (int)(i / ((long long)Kp * Np));
+        float v = 0.f;
+        if (mode == 0) { if (n < cout && k < cin) v = w[((size_t)n * cin + k) * T + t]; }
+        else           { if (n < cin && k < cout) v = w[((size_t)k * cin + n) * T + t]; }
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        dst[i] = hi;
+        if (planes > 1) dst[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the implicit-GEMM kernel
+struct TcConvParams {
+    int NB, RD, RH, RW;   // row space (fprop: output voxels; dgrad: input voxels)
+    int SD, SH;           // source spatial extents along D, H (W handled by TMA out-of-bounds fill)
+    int KD, KH, KW;
+    int sd, sh;           // strides along D and H (W stride is 1 on this path)
+    int pd, ph, pw;
+    int dgrad;
+    int Cn, Np, NT;       // true / padded column count; columns per CTA tile (<= 128)
+    int nchunks, swz;     // K chunks per tap and swizzle span in bytes (chunk = swz/2 channels)
+    int planes;           // 1 = bf16, 2 = split-bf16 x3
+    int BW, BH, halo;     // tile = BH lines x BW voxels = 128 rows; halo mode iff BH == 1
+    int tiles_w, tiles_h;
+    int DA, DB;           // ring depths
+    int a_slot_bytes, b_slot_bytes, a_plane_bytes, b_plane_bytes, a_tx_bytes;
+    int relu;
+    const float *bias, *residual;
+    float *out;
+};
+
+constexpr int kTcThreads = 192;
+
+// source line (d_src, h_src) feeding tile row-line (rd, rh0) through tap (kd, kh); false = this tap contributes nothing to the tile
+__device__ __forceinline__ bool tc_step_coords(const TcConvParams &p, int rd, int rh0, int kd, int kh, int &d_src, int &h_src) {
+    if (!p.dgrad) {
+        d_src = rd * p.sd - p.pd + kd;
+        h_src = rh0 * p.sh - p.ph + kh;              // generic mode (BH > 1) is only planned for sh == 1
+    } else {
+        const int td = rd + p.pd - kd;
+        if (td < 0 || td % p.sd != 0) return false;
+        d_src = td / p.sd;
+        const int th = rh0 + p.ph - kh;
+        if (p.BH == 1) {
+            if (th < 0 || th % p.sh != 0) return false;
+            h_src = th / p.sh;
+        } else {
+            h_src = th;                              // sh == 1
+        }
+    }
+    if (d_src < 0 || d_src >= p.SD) return false;   // whole line outside the source: zeros
+    if (h_src + p.BH <= 0 || h_src >= p.SH) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t fullA[4], emptyA[4], fullB[8], emptyB[8], accum_full;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t s_have_acc;
+    __shared__ float s_bias[128];
+
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sA = smem;
+    uint8_t *sB = smem + (size_t)p.DA * p.a_slot_bytes;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // tile decode: blockIdx.x -> (n, rd, tile_h, tile_w); blockIdx.y -> N tile
+    int t = blockIdx.x;
+    const int tw = t % p.tiles_w; t /= p.tiles_w;
+    const int th = t % p.tiles_h; t /= p.tiles_h;
+    const int rd = t % p.RD;
+    const int nb = t / p.RD;
+    const int rw0 = tw * p.BW, rh0 = th * p.BH;
+    const int n0 = blockIdx.y * p.NT;
+    const int T = p.KD * p.KH * p.KW;
+    const int chunk_elems = p.swz >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.DA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < p.DB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        mbar_init(&accum_full, 1);
+        s_have_acc = 1;
+        fence_barrier_init();
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+        const int c = threadIdx.x - 64;
+        s_bias[c] = (p.bias && n0 + c < p.Cn) ? __ldg(p.bias + n0 + c) : 0.f;
+    }
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
+    if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        // =============================================================== TMA producer
+        if (lane == 0) {
+            int itA = 0, itB = 0;
+            for (int kd = 0; kd < p.KD; ++kd)
+                for (int kh = 0; kh < p.KH; ++kh) {
+                    int d_src, h_src;
+                    if (!tc_step_coords(p, rd, rh0, kd, kh, d_src, h_src)) continue;
+                    for (int c = 0; c < p.nchunks; ++c) {
+                        if (p.halo) {
+                            const int s = itA % p.DA;
+                            mbar_wait(&emptyA[s], ((itA / p.DA) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&fullA[s], p.planes * p.a_tx_bytes);
+                            const int w_start = p.dgrad ? rw0 + p.pw - (p.KW - 1) : rw0 - p.pw;
+                            for (int pl = 0; pl < p.planes; ++pl)
+                                tma_load_5d(sA + (size_t)s * p.a_slot_bytes + (size_t)pl * p.a_plane_bytes, &tmA, &fullA[s], c * chunk_elems, w_start,
+                                            h_src, d_src, nb + pl * p.NB);
+                            ++itA;
+                        }
+                        for (int kw = 0; kw < p.KW; ++kw) {
+                            if (!p.halo) {
+                                const int s = itA % p.DA;
+                                mbar_wait(&emptyA[s], ((itA / p.DA) & 1) ^ 1);
+                                mbar_arrive_expect_tx(&fullA[s], p.planes * p.a_tx_bytes);
+                                const int w_start = p.dgrad ? rw0 + p.pw - kw : rw0 - p.pw + kw;
+                                for (int pl = 0; pl < p.planes; ++pl)
+                                    tma_load_5d(sA + (size_t)s * p.a_slot_bytes + (size_t)pl * p.a_plane_bytes, &tmA, &fullA[s], c * chunk_elems,
+                                                w_start, h_src, d_src, nb + pl * p.NB);
+                                ++itA;
+                            }
+                            const int s = itB % p.DB;
+                            mbar_wait(&emptyB[s], ((itB / p.DB) & 1) ^ 1);
+                            mbar_arrive_expect_tx(&fullB[s], p.planes * p.b_plane_bytes);
+                            const int tap = (kd * p.KH + kh) * p.KW + kw;
+                            for (int pl = 0; pl < p.planes; ++pl)
+                                tma_load_3d(sB + (size_t)s * p.b_slot_bytes + (size_t)pl * p.b_plane_bytes, &tmB, &fullB[s], c * chunk_elems, n0,
+                                            tap + pl * T);
+                            ++itB;
+                        }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        // =============================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+            const uint32_t lt = layout_type_for_swizzle_bytes(p.swz);
+            const uint32_t sbo = 8u * p.swz;
+            const int ksteps = p.swz / 32;
+            int itA = 0, itB = 0;
+            uint32_t acc = 0;
+            for (int kd = 0; kd < p.KD; ++kd)
+                for (int kh = 0; kh < p.KH; ++kh) {
+                    int d_src, h_src;
+                    if (!tc_step_coords(p, rd, rh0, kd, kh, d_src, h_src)) continue;
+                    for (int c = 0; c < p.nchunks; ++c) {
+                        int sa = itA % p.DA;
+                        if (p.halo) mbar_wait(&fullA[sa], (itA / p.DA) & 1);
+                        for (int kw = 0; kw < p.KW; ++kw) {
+                            if (!p.halo) { sa = itA % p.DA; mbar_wait(&fullA[sa], (itA / p.DA) & 1); }
+                            const int sb = itB % p.DB;
+                            mbar_wait(&fullB[sb], (itB / p.DB) & 1);
+                            tc_fence_after();
+                            const int shift = p.halo ? (p.dgrad ? p.KW - 1 - kw : kw) : 0;
+                            const uint32_t a_hi = smem_u32(sA + (size_t)sa * p.a_slot_bytes) + shift * p.swz;
+                            const uint32_t b_hi = smem_u32(sB + (size_t)sb * p.b_slot_bytes);
+                            for (int j = 0; j < ksteps; ++j) {
+                                const uint64_t da = make_smem_desc(a_hi + j * 32, 16, sbo, lt), db = make_smem_desc(b_hi + j * 32, 16, sbo, lt);
+                                umma_bf16(tmem, da, db, idesc, acc);
+                                acc = 1;
+                                if (p.planes > 1) {
+                                    umma_bf16(tmem, da, make_smem_desc(b_hi + p.b_plane_bytes + j * 32, 16, sbo, lt), idesc, 1);
+                                    umma_bf16(tmem, make_smem_desc(a_hi + p.a_plane_bytes + j * 32, 16, sbo, lt), db, idesc, 1);
+                                }
+                            }
+                            umma_commit(&emptyB[sb]);
+                            ++itB;
+                            if (!p.halo) { umma_commit(&emptyA[sa]); ++itA; }
+                        }
+                        if (p.halo) { umma_commit(&emptyA[sa]); ++itA; }
+                    }
+                }
+            if (acc) {
+                umma_commit(&accum_full);
+            } else {   // no tap contributed (e.g. a dgrad row of a strided conv that no output touches): the result is bias / zero only
+                *(volatile uint32_t *)&s_have_acc = 0;
+                mbar_arrive(&accum_full);   // release: orders the flag write before the epilogue's acquire wait
+            }
+        }
+    }
+    if (warp >= 2) {
+        // =============================================================== epilogue
+        mbar_wait(&accum_full, 0);
+        tc_fence_after();
+        const bool have_acc = (*(volatile uint32_t *)&s_have_acc) != 0u;
+        const int q = warp & 3;              // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        const int hi_ = r / p.BW, wi = r % p.BW;
+        const int rh = rh0 + hi_, rw = rw0 + wi;
+        const bool valid = rh < p.RH && rw < p.RW;
+        const size_t row_off = ((((size_t)nb * p.RD + rd) * p.RH + rh) * p.RW + rw) * (size_t)p.Cn;
+        const bool vec4 = (p.Cn % 4 == 0);
+        for (int c0 = 0; c0 < p.NT; c0 += 16) {
+            float v[16];
+            if (have_acc) {
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+            }
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                const int col = n0 + c0 + j;
+                if (col >= p.Cn) break;
+                float o[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = v[j + k] + s_bias[c0 + j + k];
+                if (vec4) {
+                    if (p.residual) {
+                        const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + row_off + col));
+                        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                    }
+                    if (p.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+                    *reinterpret_cast<float4 *>(p.out + row_off + col) = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (col + k >= p.Cn) break;
+                        float x = o[k];
+                        if (p.residual) x += __ldg(p.residual + row_off + col + k);
+                        if (p.relu) x = fmaxf(x, 0.f);
+                        p.out[row_off + col + k] = x;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcPlan {
+    bool ok = false;
+    int Kc, Kp, Nc, Np, NT, n_tiles_n, swz, nchunks, BW, BH, halo, a_rows;
+    int RD, RH, RW, SD, SH, SW;  // row space / source space
+    long long src_rows, dst_rows;
+};
+
+static TcPlan make_plan(const ConvGeom &g, int pass) {
+    TcPlan pl;
+    if (pass == 2) return pl;            // wgrad: not on this path yet
+    if (g.sw != 1) return pl;            // W stride must be 1 (halo along W)
+    const bool dgrad = pass == 1;
+    pl.Kc = dgrad ? g.cout : g.cin;
+    pl.Nc = dgrad ? g.cin : g.cout;
+    if (pl.Kc < 8) return pl;            // Cin = 1 stem etc.: bandwidth-bound direct kernel
+    pl.RD = dgrad ? g.d : g.od; pl.RH = dgrad ? g.h : g.oh; pl.RW = dgrad ? g.w : g.ow;
+    pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
+    pl.Kp = ceil_div(pl.Kc, 16) * 16;
+    pl.Np = ceil_div(pl.Nc, 16) * 16;
+    pl.NT = pl.Np <= 128 ? pl.Np : 128;
+    pl.n_tiles_n = ceil_div(pl.Np, pl.NT);
+    if (pl.Np % pl.NT) pl.Np = pl.n_tiles_n * pl.NT;   // keep the TMA box inside the packed weight tensor
+    pl.swz = (pl.Kp % 64 == 0) ? 128 : (pl.Kp % 32 == 0) ? 64 : 32;
+    pl.nchunks = pl.Kp / (pl.swz / 2);
+    if (pl.RW >= 128) { pl.BW = 128; pl.BH = 1; }
+    else {
+        int bw = 16;
+        while (bw < pl.RW) bw <<= 1;
+        if (bw > 128 || pl.RW < 8) return pl;
+        pl.BW = bw; pl.BH = 128 / bw;
+        if (g.sh != 1) return pl;        // generic mode loads BH consecutive source lines
+    }
+    pl.halo = pl.BH == 1;
+    pl.a_rows = pl.halo ? ceil_div(128 + g.kw - 1, 8) * 8 : 128;
+    if (128 + g.kw - 1 > 256) return pl;
+    pl.src_rows = (long long)g.n * pl.SD * pl.SH * pl.SW;
+    pl.dst_rows = (long long)g.n * pl.RD * pl.RH * pl.RW;
+    pl.ok = true;
+    return pl;
+}
+
+bool conv_tc_supported(const ConvGeom &g, int pass) { return make_plan(g, pass).ok && tmap_encode_fn() != nullptr; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
+    const TcPlan pl = make_plan(g, pass);
+    if (!pl.ok) return 0;
+    const int planes = precision == 1 ? 1 : 2;
+    const int T = g.kd * g.kh * g.kw;
+    return align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024) + align_up((size_t)planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
+}
+
+static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
+                       int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const TcPlan pl = make_plan(g, pass);
+    if (!pl.ok) return MDT_EUNSUPPORTED;
+    if (ws_bytes < conv_tc_workspace_bytes(g, pass, precision)) return MDT_EWORKSPACE;
+    const int planes = precision == 1 ? 1 : 2;
+    const int T = g.kd * g.kh * g.kw;
+    const bool dgrad = pass == 1;
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024));
+
+    {   // operand preparation
+        const long long total = pl.src_rows * (pl.Kp / 8);
+        long long blocks = ceil_div<long long>(total, 256);
+        if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes);
+        int rc = launch_status();
+        if (rc) return rc;
+        const long long wt = (long long)T * pl.Np * pl.Kp;
+        pack_weights_tc_kernel<<<(unsigned)ceil_div<long long>(wt, 256), 256, 0, st>>>(w, wp, g.cout, g.cin, T, pl.Np, pl.Kp, planes, dgrad ? 1 : 0);
+        if ((rc = launch_status())) return rc;
+    }
+
+    TcConvParams p{};
+    p.NB = g.n; p.RD = pl.RD; p.RH = pl.RH; p.RW = pl.RW; p.SD = pl.SD; p.SH = pl.SH;
+    p.KD = g.kd; p.KH = g.kh; p.KW = g.kw; p.sd = g.sd; p.sh = g.sh; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+    p.dgrad = dgrad ? 1 : 0;
+    p.Cn = pl.Nc; p.Np = pl.Np; p.NT = pl.NT; p.nchunks = pl.nchunks; p.swz = pl.swz; p.planes = planes;
+    p.BW = pl.BW; p.BH = pl.BH; p.halo = pl.halo;
+    p.tiles_w = ceil_div(pl.RW, pl.BW); p.tiles_h = ceil_div(pl.RH, pl.BH);
+    p.a_plane_bytes = pl.a_rows * pl.swz;
+    // the TMA writes only (128 + kw - 1) rows in halo mode; the transaction byte count must match what is written
+    const int a_rows_loaded = pl.halo ? 128 + g.kw - 1 : 128;
+    p.b_plane_bytes = pl.NT * pl.swz;
+    p.a_slot_bytes = planes * p.a_plane_bytes;
+    p.b_slot_bytes = planes * p.b_plane_bytes;
+    const int budget = 200 * 1024;
+    p.DA = pl.halo ? 3 : 4;
+    p.DB = 8;
+    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DB > 3) --p.DB;
+    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DA > 2) --p.DA;
+    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DB > 2) --p.DB;
+    if (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget) return MDT_EUNSUPPORTED;
+    p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
+
+    // tensor maps.  A: bf16 [planes*N][SD][SH][SW][Kp];  B: bf16 [planes*T][Np][Kp]
+    CUtensorMap tmA, tmB;
+    {
+        const uint64_t dims[5] = {(uint64_t)pl.Kp, (uint64_t)pl.SW, (uint64_t)pl.SH, (uint64_t)pl.SD, (uint64_t)g.n * planes};
+        const uint64_t strides[4] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.SW * pl.Kp * 2, (uint64_t)pl.SH * pl.SW * pl.Kp * 2,
+                                     (uint64_t)pl.SD * pl.SH * pl.SW * pl.Kp * 2};
+        const uint32_t box[5] = {(uint32_t)(pl.swz / 2), (uint32_t)(pl.halo ? a_rows_loaded : pl.BW), (uint32_t)pl.BH, 1u, 1u};
+        if (!encode_bf16_tmap(&tmA, xs, 5, dims, strides, box, pl.swz)) return MDT_EDRIVER;
+        const uint64_t bdims[3] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)T * planes};
+        const uint64_t bstr[2] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.Np * pl.Kp * 2};
+        const uint32_t bbox[3] = {(uint32_t)(pl.swz / 2), (uint32_t)pl.NT, 1u};
+        if (!encode_bf16_tmap(&tmB, wp, 3, bdims, bstr, bbox, pl.swz)) return MDT_EDRIVER;
+    }
+    p.a_tx_bytes = a_rows_loaded * pl.swz;   // expect_tx must equal the bytes the TMA delivers (the box), not the padded buffer pitch
+
+    const size_t smem = (size_t)p.DA * p.a_slot_bytes + (size_t)p.DB * p.b_slot_bytes + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    dim3 grid((unsigned)((long long)g.n * pl.RD * p.tiles_h * p.tiles_w), pl.n_tiles_n);
+    conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
+    return launch_status();
+}
+
+int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
+                  void *ws, size_t ws_bytes, cudaStream_t st) {
+    return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st);
+}
+int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+    return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st);
+}
 int conv_tc_wgrad(const ConvGeom &, const float *, const float *, float *, float *, int, void *, size_t, cudaStream_t) { return MDT_EUNSUPPORTED; }
+
 }  // namespace mdt

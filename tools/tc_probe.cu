@@ -4,6 +4,8 @@
 //   kmajor  sw in {128, 64, 32}          K-major operands, K split into swizzle-span chunks (what fprop/dgrad use)
 //   shift   row offset s in {1, 2, 5}    A descriptor starts s rows into a taller tile (halo reuse), base_offset 0 vs (s & 7)
 //   mnmajor sw in {128, 64, 32}          both operands MN-major: A^T [K x 128], B^T [K x N] tiles (what wgrad uses)
+//   mnshift sw in {128, 64}              MN-major B whose N index runs over 3 row-shifted windows of one halo tile (LBO = one row):
+//                                        D[m][s*chunk + c] = sum_k A[m][k] * Bt[k + s][c]   (wgrad: all kw taps in one MMA)
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -31,10 +33,10 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
     const int nchunks_k = p.K / chunk;          // K-major: chunks along K
     // K-major: A chunk buffers [a_rows][chunk] each a_rows*sw bytes; B chunk buffers [N][chunk]
     // MN-major: A buffers: for each 'chunk'-wide slice of M (128/chunk slices): [K rows][chunk]; B: N/chunk slices of [K][chunk]
-    const uint32_t a_chunk_bytes = (p.mode == 2 ? p.K : p.a_rows) * p.sw;
-    const uint32_t b_chunk_bytes = (p.mode == 2 ? p.K : p.N) * p.sw;
-    const int a_nbuf = p.mode == 2 ? 128 / chunk : nchunks_k;
-    const int b_nbuf = p.mode == 2 ? p.N / chunk : nchunks_k;
+    const uint32_t a_chunk_bytes = (p.mode >= 2 ? p.K : p.a_rows) * p.sw;
+    const uint32_t b_chunk_bytes = (p.mode == 3 ? p.K + 8 : p.mode == 2 ? p.K : p.N) * p.sw;
+    const int a_nbuf = p.mode >= 2 ? 128 / chunk : nchunks_k;
+    const int b_nbuf = p.mode == 3 ? 1 : p.mode == 2 ? p.N / chunk : nchunks_k;
     uint8_t *sA = smem;
     uint8_t *sB = smem + ((a_nbuf * a_chunk_bytes + 1023) / 1024) * 1024;
     if (threadIdx.x == 0) {
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
         mbar_wait(&bar_full, 0);
         tc_fence_after();
         const uint32_t lt = layout_type_for_swizzle_bytes(p.sw);
-        if (p.mode != 2) {
+        if (p.mode < 2) {
             const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
             const uint32_t sbo = 8 * p.sw;
             int acc = 0;
@@ -73,8 +75,8 @@ __global__ void __launch_bounds__(128) probe_kernel(const __grid_constant__ CUte
             for (int k = 0; k < p.K / 16; ++k) {
                 const uint32_t a_addr = smem_u32(sA) + k * 16 * p.sw;
                 const uint32_t b_addr = smem_u32(sB) + k * 16 * p.sw;
-                umma_bf16(tmem, make_smem_desc(a_addr, a_chunk_bytes, 8 * p.sw, lt, 0), make_smem_desc(b_addr, b_chunk_bytes, 8 * p.sw, lt, 0),
-                          idesc, acc);
+                const uint32_t b_lbo = p.mode == 3 ? (uint32_t)p.sw : b_chunk_bytes;   // mode 3: next N chunk = next ROW of the halo tile
+                umma_bf16(tmem, make_smem_desc(a_addr, a_chunk_bytes, 8 * p.sw, lt, 0), make_smem_desc(b_addr, b_lbo, 8 * p.sw, lt, 0), idesc, acc);
                 acc = 1;
             }
         }
@@ -98,20 +100,27 @@ static float bf(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 static int run(const char *name, ProbeParams p) {
     const int M = 128, rowsA = p.a_rows;
-    std::vector<float> A((size_t)rowsA * p.K), B((size_t)p.N * p.K);
+    const int chunk_h = p.sw / 2;
+    std::vector<float> A((size_t)rowsA * p.K), B((size_t)(p.mode == 3 ? chunk_h * (p.K + 8) : p.N * p.K));
     srand(1234 + p.sw + p.mode * 7 + p.shift);
     for (auto &v : A) v = bf((rand() % 2001 - 1000) / 1000.f);
     for (auto &v : B) v = bf((rand() % 2001 - 1000) / 1000.f);
     // device layouts: K-major: A[rowsA][K], B[N][K];  MN-major: At[K][M], Bt[K][N]
     std::vector<__nv_bfloat16> hA, hB;
-    if (p.mode != 2) {
+    if (p.mode < 2) {
         hA.resize(A.size()); hB.resize(B.size());
         for (size_t i = 0; i < A.size(); ++i) hA[i] = __float2bfloat16(A[i]);
         for (size_t i = 0; i < B.size(); ++i) hB[i] = __float2bfloat16(B[i]);
     } else {
-        hA.resize((size_t)p.K * M); hB.resize((size_t)p.K * p.N);
+        hA.resize((size_t)p.K * M);
         for (int m = 0; m < M; ++m) for (int k = 0; k < p.K; ++k) hA[(size_t)k * M + m] = __float2bfloat16(A[(size_t)m * p.K + k]);
-        for (int n = 0; n < p.N; ++n) for (int k = 0; k < p.K; ++k) hB[(size_t)k * p.N + n] = __float2bfloat16(B[(size_t)n * p.K + k]);
+        if (p.mode == 2) {
+            hB.resize((size_t)p.K * p.N);
+            for (int n = 0; n < p.N; ++n) for (int k = 0; k < p.K; ++k) hB[(size_t)k * p.N + n] = __float2bfloat16(B[(size_t)n * p.K + k]);
+        } else {   // mode 3: Bt halo [K + 8][chunk], stored as is
+            hB.resize(B.size());
+            for (size_t i = 0; i < B.size(); ++i) hB[i] = __float2bfloat16(B[i]);
+        }
     }
     __nv_bfloat16 *dA, *dB; float *dOut;
     cudaMalloc(&dA, hA.size() * 2); cudaMalloc(&dB, hB.size() * 2); cudaMalloc(&dOut, (size_t)M * p.N * 4);
@@ -121,7 +130,7 @@ static int run(const char *name, ProbeParams p) {
     CUtensorMap tmA, tmB;
     const int chunk = p.sw / 2;
     bool ok;
-    if (p.mode != 2) {
+    if (p.mode < 2) {
         uint64_t dimsA[2] = {(uint64_t)p.K, (uint64_t)rowsA}, strA[1] = {(uint64_t)p.K * 2};
         uint32_t boxA[2] = {(uint32_t)chunk, (uint32_t)rowsA};
         uint64_t dimsB[2] = {(uint64_t)p.K, (uint64_t)p.N}, strB[1] = {(uint64_t)p.K * 2};
@@ -130,8 +139,8 @@ static int run(const char *name, ProbeParams p) {
     } else {
         uint64_t dimsA[2] = {(uint64_t)M, (uint64_t)p.K}, strA[1] = {(uint64_t)M * 2};
         uint32_t boxA[2] = {(uint32_t)chunk, (uint32_t)p.K};
-        uint64_t dimsB[2] = {(uint64_t)p.N, (uint64_t)p.K}, strB[1] = {(uint64_t)p.N * 2};
-        uint32_t boxB[2] = {(uint32_t)chunk, (uint32_t)p.K};
+        uint64_t dimsB[2] = {(uint64_t)(p.mode == 3 ? chunk : p.N), (uint64_t)(p.mode == 3 ? p.K + 8 : p.K)}, strB[1] = {(uint64_t)(p.mode == 3 ? chunk : p.N) * 2};
+        uint32_t boxB[2] = {(uint32_t)chunk, (uint32_t)(p.mode == 3 ? p.K + 8 : p.K)};
         ok = encode_bf16_tmap(&tmA, dA, 2, dimsA, strA, boxA, p.sw) && encode_bf16_tmap(&tmB, dB, 2, dimsB, strB, boxB, p.sw);
     }
     if (!ok) { printf("%-28s ENCODE_FAILED\n", name); return 1; }
@@ -146,7 +155,8 @@ static int run(const char *name, ProbeParams p) {
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < p.N; ++n) {
             double r = 0;
-            for (int k = 0; k < p.K; ++k) r += (double)A[(size_t)(m + p.shift) * p.K + k] * B[(size_t)n * p.K + k];
+            if (p.mode == 3) { const int sft = n / chunk, c = n % chunk; for (int k = 0; k < p.K; ++k) r += (double)A[(size_t)m * p.K + k] * B[(size_t)(k + sft) * chunk + c]; }
+            else for (int k = 0; k < p.K; ++k) r += (double)A[(size_t)(m + p.shift) * p.K + k] * B[(size_t)n * p.K + k];
             maxerr = fmax(maxerr, fabs(r - out[(size_t)m * p.N + n]));
             maxref = fmax(maxref, fabs(r));
         }
@@ -177,6 +187,12 @@ int main() {
         run(name, ProbeParams{64, 64, sw, 2, 0, 0, 128});
         snprintf(name, sizeof name, "mnmajor_sw%d_N128_K32", sw);
         run(name, ProbeParams{128, 32, sw, 2, 0, 0, 128});
+    }
+    for (int sw : {128, 64}) {
+        snprintf(name, sizeof name, "mnshift_sw%d_N%d_K64", sw, 3 * sw / 2);
+        run(name, ProbeParams{3 * sw / 2, 64, sw, 3, 0, 0, 128});
+        snprintf(name, sizeof name, "mnshift_sw%d_N%d_K128", sw, 3 * sw / 2);
+        run(name, ProbeParams{3 * sw / 2, 128, sw, 3, 0, 0, 128});
     }
     printf("kmajor failures: %d\n", bad);
     return 0;
