@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restric
                                                         int *__restrict__ row_argmax, unsigned long long *__restrict__ col_max_key) {
     constexpr int B = 2 * DIM;
     __shared__ double s_gt[kMaxGtSmem * (B + 1)];
+    __shared__ unsigned long long s_colmax[kMaxGtSmem];
+    const unsigned long long key_zero = ordered_key(0.0);   // column maxima start at IoU 0 (every IoU is >= 0): zero overlaps never touch an atomic
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = a < A;
     double box[B];
@@ -71,6 +73,7 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restric
 #pragma unroll
             for (int k = 0; k < B; ++k) { gb[k] = gt[(size_t)(g0 + i) * B + k]; s_gt[i * (B + 1) + k] = gb[k]; }
             s_gt[i * (B + 1) + B] = box_volume<DIM>(gb);
+            s_colmax[i] = key_zero;
         }
         __syncthreads();
         for (int i = 0; i < gn; ++i) {
@@ -84,8 +87,11 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restric
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other > key ? other : key;
             }
-            if ((threadIdx.x & 31) == 0 && key != 0ULL) atomicMax(col_max_key + g0 + i, key);
+            if ((threadIdx.x & 31) == 0 && key > key_zero) atomicMax(&s_colmax[i], key);   // warp max -> block max (shared memory)
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < gn; i += blockDim.x)
+            if (s_colmax[i] > key_zero) atomicMax(col_max_key + g0 + i, s_colmax[i]);             // one global atomic per block and GT at most
     }
     if (live) row_argmax[a] = best_g;
 }
@@ -105,7 +111,9 @@ __global__ void __launch_bounds__(256) match_cols_kernel(const double *__restric
 #pragma unroll
         for (int k = 0; k < B; ++k) gb[k] = __ldg(gt + (size_t)g * B + k);
         const double v = iou_f64<DIM>(gb, box_volume<DIM>(gb), box, va);
-        if (ordered_key(v) == __ldg(col_max_key + g)) atomicMin(col_argmax + g, a);  // first anchor on ties (np.argmax axis=0)
+        // first anchor on ties (np.argmax axis=0).  A column whose maximum is 0 is won by anchor 0 by definition: resolved in finalize.
+        const unsigned long long cm = __ldg(col_max_key + g);
+        if (cm != ordered_key(0.0) && ordered_key(v) == cm) atomicMin(col_argmax + g, a);
     }
 }
 
@@ -113,7 +121,8 @@ template <int DIM>
 __global__ void __launch_bounds__(256) match_finalize_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt,
                                                             const int *__restrict__ gt_cls, int G, double neg_t, double pos_t,
                                                             const int *__restrict__ row_argmax, const int *__restrict__ col_argmax,
-                                                            int *__restrict__ matches, int *__restrict__ n_pos) {
+                                                            const unsigned long long *__restrict__ col_max_key, int *__restrict__ matches,
+                                                            int *__restrict__ n_pos) {
     constexpr int B = 2 * DIM;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     int label = 0;
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const double *__res
         const double mx = iou_f64<DIM>(gb, box_volume<DIM>(gb), box, box_volume<DIM>(box));
         if (mx < neg_t) label = -1;                                       // step 1
         for (int g = 0; g < G; ++g)                                        // step 2, ascending: later GT overwrites
-            if (__ldg(col_argmax + g) == a) label = gt_cls ? __ldg(gt_cls + g) : 1;
+            if ((__ldg(col_max_key + g) == ordered_key(0.0) ? 0 : __ldg(col_argmax + g)) == a) label = gt_cls ? __ldg(gt_cls + g) : 1;
         if (mx >= pos_t) label = gt_cls ? __ldg(gt_cls + ga) : 1;         // step 3
         matches[a] = label;
     }
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(256) match_finalize_kernel(const double *__res
 
 __global__ void match_init_kernel(unsigned long long *col_max_key, int *col_argmax, int G, int *n_pos) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g < G) { col_max_key[g] = 0ULL; col_argmax[g] = 0x7fffffff; }
+    if (g < G) { col_max_key[g] = ordered_key(0.0); col_argmax[g] = 0x7fffffff; }
     if (g == 0) *n_pos = 0;
 }
 
@@ -186,7 +195,7 @@ static int anchor_match_impl(const double *anchors, int A, const double *gt, con
     if ((rc = launch_status())) return rc;
     match_cols_kernel<DIM><<<blocks, 256, 0, st>>>(anchors, A, gt, G, col_max_key, col_argmax);
     if ((rc = launch_status())) return rc;
-    match_finalize_kernel<DIM><<<blocks, 256, 0, st>>>(anchors, A, gt, gt_cls, G, neg_t, pos_t, row_argmax, col_argmax, matches, n_pos);
+    match_finalize_kernel<DIM><<<blocks, 256, 0, st>>>(anchors, A, gt, gt_cls, G, neg_t, pos_t, row_argmax, col_argmax, col_max_key, matches, n_pos);
     return launch_status();
 }
 

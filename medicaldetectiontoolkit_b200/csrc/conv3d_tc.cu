@@ -418,7 +418,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
 
     const size_t smem = (size_t)p.DA * p.a_slot_bytes + (size_t)p.DB * p.b_slot_bytes + 1024;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr = true; }
+    if (!attr) { if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER; attr = true; }
     dim3 grid((unsigned)((long long)g.n * pl.RD * p.tiles_h * p.tiles_w), pl.n_tiles_n);
     conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
     return launch_status();

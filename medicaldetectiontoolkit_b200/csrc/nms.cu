@@ -54,84 +54,96 @@ __device__ __forceinline__ bool suppresses(const float *a, float Sa, const float
     return __fdiv_rn(inter, uni) > thresh;
 }
 
-// grid: (col_block, row_block) over the UPPER triangle only (col_block >= row_block); lower-triangle words are never read by the
-// reduction, but mdt_nms_mask_* (reference `_nms` contract: every word written) launches with full=1.
+// One CTA per row block (64 boxes held in registers, one per lane of each of the 4 column groups); the 4 groups of 64 threads walk the
+// column tiles rb, rb+1, ... four at a time (upper triangle only unless `full`, which reproduces the reference `_nms` contract where the
+// lower triangle is computed too, nms_kernel.cu:35 being commented out).  Column tiles are staged in shared memory with coalesced loads;
+// the four groups write four ADJACENT mask words of each row in the same iteration, so every 32-byte sector of the mask is completed
+// within one iteration.  Heaviest row blocks (most column tiles) are scheduled first.
+constexpr int kMaskGroups = 4;
+
 template <int DIM>
-__global__ void __launch_bounds__(kTile) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
-                                                        unsigned long long *__restrict__ mask, int col_blocks, int full) {
+__global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
+                                                                    unsigned long long *__restrict__ mask, int col_blocks, int full) {
     constexpr int F = BoxF<DIM>::n;
-    const int row_blk = blockIdx.y, col_blk = blockIdx.x;
-    if (!full && col_blk < row_blk) return;
+    const int row_blk = blockIdx.x;
+    const int group = threadIdx.x / kTile, t = threadIdx.x % kTile;
     const int row_size = min(n - row_blk * kTile, kTile);
-    const int col_size = min(n - col_blk * kTile, kTile);
-    __shared__ float tile[kTile * F];
-    // coalesced tile load: kTile*F consecutive floats
-    for (int i = threadIdx.x; i < col_size * F; i += kTile) tile[i] = boxes[(size_t)col_blk * kTile * F + i];
-    __syncthreads();
-    if ((int)threadIdx.x < row_size) {
-        const int cur = row_blk * kTile + threadIdx.x;
-        float a[F];
+    __shared__ float tile[kMaskGroups][kTile * F];
+    const int cur = row_blk * kTile + t;
+    const bool row_live = t < row_size;
+    float a[F];
 #pragma unroll
-        for (int k = 0; k < F - 1; ++k) a[k] = boxes[(size_t)cur * F + k];
-        const float Sa = box_volume_a(a, DIM);
-        const bool fast = thresh >= 0.f;
-        unsigned long long t = 0;
-        int start = (row_blk == col_blk) ? threadIdx.x + 1 : 0;
-        if (!full || col_blk >= row_blk) {
+    for (int k = 0; k < F - 1; ++k) a[k] = row_live ? boxes[(size_t)cur * F + k] : 0.f;
+    const float Sa = box_volume_a(a, DIM);
+    const bool fast = thresh >= 0.f;
+    const int c_begin = full ? 0 : row_blk;
+    for (int c0 = c_begin; c0 < col_blocks; c0 += kMaskGroups) {
+        const int col_blk = c0 + group;
+        const bool live = col_blk < col_blocks;
+        const int col_size = live ? min(n - col_blk * kTile, kTile) : 0;
+        for (int i = t; i < col_size * F; i += kTile) tile[group][i] = boxes[(size_t)col_blk * kTile * F + i];
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kTile) : "memory");   // group-local barrier
+        if (live && row_live) {
+            unsigned long long word = 0;
+            const int start = (row_blk == col_blk) ? t + 1 : 0;   // a box may only suppress LOWER-scored boxes of its own block
             for (int i = start; i < col_size; ++i)
-                if (suppresses<DIM>(a, Sa, tile + i * F, thresh, fast)) t |= 1ULL << i;
-        } else {
-            // lower triangle requested by the `_nms`-compatible entry point: the reference computes it too (nms_kernel.cu:35 is commented out)
-            for (int i = 0; i < col_size; ++i)
-                if (suppresses<DIM>(a, Sa, tile + i * F, thresh, fast)) t |= 1ULL << i;
+                if (suppresses<DIM>(a, Sa, tile[group] + i * F, thresh, fast)) word |= 1ULL << i;
+            mask[(size_t)cur * col_blocks + col_blk] = word;
         }
-        mask[(size_t)cur * col_blocks + col_blk] = t;
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kTile) : "memory");
     }
 }
 
-// Greedy reduction on one CTA. remv (the suppression bitmap) lives in shared memory; boxes are consumed 64 at a time:
-//   (1) one thread resolves the 64 keep decisions of the block from the diagonal mask word of each box (serial, registers/smem only),
-//   (2) all threads OR the mask rows of the boxes just kept into remv for the remaining column words (coalesced 8-byte loads).
-// This is the exact recurrence of nms_cuda.c:47-58.
+// Greedy reduction on one CTA — the exact recurrence of nms_cuda.c:47-58 with remv (the suppression bitmap) in shared memory.
+// Boxes are consumed 64 at a time:
+//   (1) one thread resolves the 64 keep decisions of the block from the 64 diagonal mask words (registers / shared memory only);
+//   (2) the 1024 threads, arranged as 64 rows x 16 word-lanes, OR the mask rows of the boxes just kept into remv: every thread streams
+//       its strided share of a row with independent 8-byte loads (several in flight) and touches remv only for non-zero words.
+// The diagonal words of the NEXT block do not depend on remv and are prefetched during (2).
 constexpr int kScanThreads = 1024;
+constexpr int kScanLanes = kScanThreads / kTile;   // 16 word-lanes per row
 
 __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_blocks, const unsigned long long *__restrict__ mask,
                                                                int64_t *__restrict__ keep, int *__restrict__ num_out) {
     extern __shared__ unsigned long long remv[];  // [col_blocks]
-    __shared__ unsigned long long diag[kTile];
+    __shared__ unsigned long long diag[2][kTile];
     __shared__ unsigned long long s_kept;
     __shared__ int s_count;
     for (int j = threadIdx.x; j < col_blocks; j += kScanThreads) remv[j] = 0ULL;
     if (threadIdx.x == 0) s_count = 0;
+    if ((int)threadIdx.x < min(n, kTile)) diag[0][threadIdx.x] = mask[(size_t)threadIdx.x * col_blocks];
     __syncthreads();
+    const int r = threadIdx.x / kScanLanes, l = threadIdx.x % kScanLanes;
     for (int b = 0; b < col_blocks; ++b) {
         const int base = b * kTile;
         const int size = min(n - base, kTile);
-        if ((int)threadIdx.x < size) diag[threadIdx.x] = mask[(size_t)(base + threadIdx.x) * col_blocks + b];
-        __syncthreads();
+        const unsigned long long *dg = diag[b & 1];
         if (threadIdx.x == 0) {
-            unsigned long long r = remv[b], kept = 0ULL;
+            unsigned long long rm = remv[b], kept = 0ULL;
             int cnt = s_count;
             for (int i = 0; i < size; ++i) {
-                if (!((r >> i) & 1ULL)) {
+                if (!((rm >> i) & 1ULL)) {
                     kept |= 1ULL << i;
                     keep[cnt++] = base + i;
-                    r |= diag[i];
+                    rm |= dg[i];
                 }
             }
             s_kept = kept;
             s_count = cnt;
         }
+        // prefetch the next block's diagonal words (independent of remv)
+        if (b + 1 < col_blocks && (int)threadIdx.x >= kScanThreads - kTile) {
+            const int i = threadIdx.x - (kScanThreads - kTile);
+            if (base + kTile + i < n) diag[(b + 1) & 1][i] = mask[(size_t)(base + kTile + i) * col_blocks + b + 1];
+        }
         __syncthreads();
-        const unsigned long long kept = s_kept;
-        for (int j = b + 1 + threadIdx.x; j < col_blocks; j += kScanThreads) {
-            unsigned long long acc = 0ULL, k = kept;
-            while (k) {
-                int i = __ffsll((long long)k) - 1;
-                k &= k - 1;
-                acc |= mask[(size_t)(base + i) * col_blocks + j];
+        if ((s_kept >> r) & 1ULL) {
+            const unsigned long long *row = mask + (size_t)(base + r) * col_blocks;
+#pragma unroll 4
+            for (int j = b + 1 + l; j < col_blocks; j += kScanLanes) {
+                const unsigned long long v = row[j];
+                if (v) atomicOr(&remv[j], v);
             }
-            remv[j] |= acc;
         }
         __syncthreads();
     }
@@ -143,9 +155,7 @@ static int launch_mask(int n, const float *boxes, unsigned long long *mask, floa
     if (n < 0 || (n > 0 && (!boxes || !mask))) return MDT_EINVAL;
     if (n == 0) return MDT_OK;
     const int cb = ceil_div(n, kTile);
-    if (cb > 65535) return MDT_EUNSUPPORTED;  // grid.y limit: N <= 4.19 M boxes
-    dim3 grid(cb, cb);
-    nms_mask_kernel<DIM><<<grid, kTile, 0, st>>>(n, thresh, boxes, mask, cb, full);
+    nms_mask_kernel<DIM><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
     return launch_status();
 }
 
