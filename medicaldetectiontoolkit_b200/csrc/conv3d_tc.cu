@@ -343,11 +343,18 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     return pl;
 }
 
-bool conv_tc_supported(const ConvGeom &g, int pass) { return make_plan(g, pass).ok && tmap_encode_fn() != nullptr; }
+bool conv_tc_wgrad_supported(const ConvGeom &g);
+size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision);
+
+bool conv_tc_supported(const ConvGeom &g, int pass) {
+    if (pass == 2) return conv_tc_wgrad_supported(g);
+    return make_plan(g, pass).ok && tmap_encode_fn() != nullptr;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
+    if (pass == 2) return conv_tc_wgrad_workspace_bytes(g, precision);
     const TcPlan pl = make_plan(g, pass);
     if (!pl.ok) return 0;
     const int planes = precision == 1 ? 1 : 2;
@@ -431,6 +438,5 @@ int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float
 int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
     return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st);
 }
-int conv_tc_wgrad(const ConvGeom &, const float *, const float *, float *, float *, int, void *, size_t, cudaStream_t) { return MDT_EUNSUPPORTED; }
 
 }  // namespace mdt

@@ -1,0 +1,337 @@
+// conv3d weight gradient on tcgen05 (algo 2, pass 2):  dw[co, ci, tap] = sum_voxels dy[v, co] * x[src(v, tap), ci].
+//
+// GEMM view: for each tap, D[M = co][N = ci] accumulates over K = voxels.  Both operands are "MN-major" in shared memory: the TMA
+// drops a line of voxels as [voxel rows][channels] tiles, which is exactly the transposed (MN-major) canonical layout of tcgen05.
+//
+// Two B200-specific tricks (both verified by tools/tc_probe on hardware, profiles/r01_tc_probe*.txt):
+//  * all kw taps of a (kd, kh) pair in ONE MMA: the x operand is a halo line of (voxels + kw - 1) rows; its N index runs over kw
+//    row-shifted windows of that single buffer by setting the descriptor's leading-dimension byte offset to ONE ROW, N = kw * chunk;
+//  * split-bf16 in 2 MMAs instead of 3: the dy operand's M = 128 rows are [dy_hi | dy_lo] (the two bf16 planes sit in adjacent
+//    shared-memory chunks), so one MMA against x_hi and one against x_lo produce hi*hi + hi*lo in TMEM lanes [0, co) and
+//    lo*hi + lo*lo in lanes [co_p, co_p + co); the epilogue adds both halves into dw.  (Used when 2 * co_p <= 128; otherwise 3 MMAs.)
+//
+// Work decomposition: a CTA owns up to CB "column blocks" (kd, kh, ci-chunk) whose accumulators fill its 512 TMEM columns, and a
+// strided share of the output lines; it streams dy lines + x halo lines through a 2-stage TMA ring and finally reduces its partial
+// dw with fp32 red.global.add.
+#include "conv3d_common.cuh"
+#include "tc_common.cuh"
+
+namespace mdt {
+using namespace tc;
+
+__global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes);
+
+struct TcWgradParams {
+    int NB, OD, OH, OW, D, H, W;
+    int KD, KH, KW, sd, sh, pd, ph, pw;
+    int cin, cout, T;
+    int seg, segs, ksteps;           // voxels per work unit (<= 128), units per line, K16 steps
+    int swy, chunky, nmc, co_p;      // dy: swizzle bytes, channels per chunk, chunks in one M tile, padded cout
+    int mtrick;
+    int swx, chunkx, nxc;            // x: swizzle bytes, channels per chunk, number of ci chunks
+    int ncb_total, CB, groups, splits;
+    int planes;
+    int y_chunk_bytes, y_plane_bytes, x_plane_bytes, x_buf_bytes, stage_bytes;
+    int y_tx_bytes, x_tx_bytes;      // bytes one TMA box delivers
+    long long units;                 // NB * OD * OH * segs
+    float *dw;
+};
+
+constexpr int kWgThreads = 192;
+constexpr int kWgStages = 2;
+
+__device__ __forceinline__ void wg_decode_cb(const TcWgradParams &p, int cb, int &kd, int &kh, int &xc) {
+    xc = cb % p.nxc;
+    const int pair = cb / p.nxc;
+    kh = pair % p.KH;
+    kd = pair / p.KH;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t full[kWgStages], empty[kWgStages], accum_full;
+    __shared__ uint32_t tmem_base_s, s_started;
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x % p.groups, split = blockIdx.x / p.groups;
+    const int mt = blockIdx.y;                       // M tile (128 rows of co) when co_p > 128
+    const int cb0 = group * p.CB;
+    const int ncb = min(p.CB, p.ncb_total - cb0);
+    const int ncols = p.KW * p.chunkx;               // accumulator columns per column block
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(&accum_full, 1);
+        s_started = 0;
+        fence_barrier_init();
+        prefetch_tmap(&tmY);
+        prefetch_tmap(&tmX);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    // unit -> (n, od, oh, seg)
+    auto decode_unit = [&](long long u, int &n, int &od, int &oh, int &ow0) {
+        const int sg = (int)(u % p.segs); u /= p.segs;
+        oh = (int)(u % p.OH); u /= p.OH;
+        od = (int)(u % p.OD);
+        n = (int)(u / p.OD);
+        ow0 = sg * p.seg;
+    };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;
+            for (long long u = split; u < p.units; u += p.splits, ++it) {
+                int n, od, oh, ow0;
+                decode_unit(u, n, od, oh, ow0);
+                const int s = it % kWgStages;
+                mbar_wait(&empty[s], ((it / kWgStages) & 1) ^ 1);
+                uint8_t *st = smem + (size_t)s * p.stage_bytes;
+                // which column blocks have their source line inside the image
+                uint32_t bytes = p.planes * p.nmc * p.y_tx_bytes;
+                for (int b = 0; b < ncb; ++b) {
+                    int kd, kh, xc;
+                    wg_decode_cb(p, cb0 + b, kd, kh, xc);
+                    const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
+                    if (d >= 0 && d < p.D && h >= 0 && h < p.H) bytes += p.planes * p.x_tx_bytes;
+                }
+                mbar_arrive_expect_tx(&full[s], bytes);
+                for (int pl = 0; pl < p.planes; ++pl)
+                    for (int mc = 0; mc < p.nmc; ++mc)
+                        tma_load_5d(st + (size_t)pl * p.y_plane_bytes + (size_t)mc * p.y_chunk_bytes, &tmY, &full[s], (mt * p.nmc + mc) * p.chunky, ow0,
+                                    oh, od, n + pl * p.NB);
+                uint8_t *xb = st + (size_t)p.planes * p.y_plane_bytes;
+                for (int b = 0; b < ncb; ++b) {
+                    int kd, kh, xc;
+                    wg_decode_cb(p, cb0 + b, kd, kh, xc);
+                    const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
+                    if (d < 0 || d >= p.D || h < 0 || h >= p.H) continue;
+                    for (int pl = 0; pl < p.planes; ++pl)
+                        tma_load_5d(xb + (size_t)b * p.x_buf_bytes + (size_t)pl * p.x_plane_bytes, &tmX, &full[s], xc * p.chunkx, ow0 - p.pw, h, d,
+                                    n + pl * p.NB);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
+            const uint32_t lty = layout_type_for_swizzle_bytes(p.swy), ltx = layout_type_for_swizzle_bytes(p.swx);
+            uint32_t started = 0;
+            int it = 0;
+            for (long long u = split; u < p.units; u += p.splits, ++it) {
+                int n, od, oh, ow0;
+                decode_unit(u, n, od, oh, ow0);
+                const int s = it % kWgStages;
+                mbar_wait(&full[s], (it / kWgStages) & 1);
+                tc_fence_after();
+                const uint32_t y_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
+                const uint32_t x0 = y_hi + p.planes * p.y_plane_bytes;
+                for (int b = 0; b < ncb; ++b) {
+                    int kd, kh, xc;
+                    wg_decode_cb(p, cb0 + b, kd, kh, xc);
+                    const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
+                    if (d < 0 || d >= p.D || h < 0 || h >= p.H) continue;
+                    const uint32_t xb = x0 + b * p.x_buf_bytes;
+                    const uint32_t dcol = tmem + b * ncols;
+                    uint32_t acc = (started >> b) & 1u;
+                    for (int k = 0; k < p.ksteps; ++k) {
+                        const uint32_t ya = y_hi + k * 16 * p.swy, xa = xb + k * 16 * p.swx;
+                        const uint64_t dy_hi = make_smem_desc(ya, p.y_chunk_bytes, 8 * p.swy, lty);
+                        const uint64_t dx_hi = make_smem_desc(xa, p.swx, 8 * p.swx, ltx);      // LBO = one row: next N chunk = next kw shift
+                        umma_bf16(dcol, dy_hi, dx_hi, idesc, acc);
+                        acc = 1;
+                        if (p.planes > 1) {
+                            const uint64_t dx_lo = make_smem_desc(xa + p.x_plane_bytes, p.swx, 8 * p.swx, ltx);
+                            umma_bf16(dcol, dy_hi, dx_lo, idesc, 1);
+                            if (!p.mtrick) umma_bf16(dcol, make_smem_desc(ya + p.y_plane_bytes, p.y_chunk_bytes, 8 * p.swy, lty), dx_hi, idesc, 1);
+                        }
+                    }
+                    started |= 1u << b;
+                }
+                umma_commit(&empty[s]);
+            }
+            *(volatile uint32_t *)&s_started = started;
+            __threadfence_block();
+            if (started) umma_commit(&accum_full);
+            else mbar_arrive(&accum_full);
+        }
+    }
+    if (warp >= 2) {
+        mbar_wait(&accum_full, 0);
+        tc_fence_after();
+        const uint32_t started = *(volatile uint32_t *)&s_started;
+        const int q = warp & 3;
+        const int m = q * 32 + lane;   // TMEM lane = row of D
+        // which cout does this lane hold?  mtrick: lanes [0, co_p) = hi part, [co_p, 2 co_p) = lo part (same cout), rest unused
+        int co = -1;
+        if (p.mtrick) { if (m < 2 * p.co_p) co = m % p.co_p; }
+        else co = mt * 128 + m;
+        const bool co_ok = co >= 0 && co < p.cout;
+        for (int b = 0; b < ncb; ++b) {
+            if (!((started >> b) & 1u)) continue;
+            int kd, kh, xc;
+            wg_decode_cb(p, cb0 + b, kd, kh, xc);
+            for (int c0 = 0; c0 < ncols; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * ncols + c0, v);
+                tmem_ld_wait();
+                if (!co_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = c0 + j;
+                    const int kw = col / p.chunkx, ci = xc * p.chunkx + col % p.chunkx;
+                    if (ci < p.cin && v[j] != 0.f)
+                        atomicAdd(p.dw + ((size_t)co * p.cin + ci) * p.T + (kd * p.KH + kh) * p.KW + kw, v[j]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+struct WgPlan {
+    bool ok = false;
+    int co_p, swy, chunky, nmc, mtiles, mtrick;
+    int ci_p, swx, chunkx, nxc;
+    int seg, segs, ksteps, rows_y, rows_x, rows_x_pad;
+    int ncb_total, CB, groups;
+};
+
+static WgPlan make_wg_plan(const ConvGeom &g) {
+    WgPlan w;
+    if (g.sw != 1) return w;
+    if (g.cin < 8 || g.cout < 8) return w;
+    // x (N side): one chunk spans all of ci when ci <= 64, so that all kw taps of a pair fit one MMA
+    w.ci_p = g.cin <= 16 ? 16 : g.cin <= 32 ? 32 : ceil_div(g.cin, 64) * 64;
+    w.chunkx = w.ci_p < 64 ? w.ci_p : 64;
+    w.swx = w.chunkx * 2;
+    w.nxc = w.ci_p / w.chunkx;
+    if (g.kw * w.chunkx > 256) return w;
+    // dy (M side)
+    w.co_p = ceil_div(g.cout, 16) * 16;
+    w.swy = (w.co_p % 64 == 0) ? 128 : (w.co_p % 32 == 0) ? 64 : 32;
+    w.chunky = w.swy / 2;
+    w.mtrick = (2 * w.co_p <= 128) ? 1 : 0;
+    if (w.mtrick) { w.nmc = w.co_p / w.chunky; w.mtiles = 1; }
+    else {
+        // M tiles of 128 rows; pad cout to a multiple of 128 so every tile has 128 / chunky chunks
+        w.co_p = ceil_div(g.cout, 128) * 128;
+        w.swy = 128; w.chunky = 64;
+        w.nmc = 2; w.mtiles = w.co_p / 128;
+    }
+    w.seg = g.ow >= 128 ? 128 : g.ow;
+    w.segs = ceil_div(g.ow, w.seg);
+    w.ksteps = ceil_div(w.seg, 16);
+    w.rows_y = w.ksteps * 16;
+    w.rows_x = w.ksteps * 16 + g.kw - 1;
+    w.rows_x_pad = ceil_div(w.rows_x, 8) * 8;
+    if (w.rows_x > 256) return w;
+    w.ncb_total = g.kd * g.kh * w.nxc;
+    w.CB = 512 / (g.kw * w.chunkx);
+    if (w.CB > 32) w.CB = 32;
+    if (w.CB > w.ncb_total) w.CB = w.ncb_total;
+    // shared memory: 2 stages of (dy planes + CB x buffers)
+    auto stage_bytes = [&](int cb, int planes) { return planes * w.nmc * w.rows_y * w.swy + cb * planes * w.rows_x_pad * w.swx; };
+    while (w.CB > 1 && kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) --w.CB;
+    if (kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) return w;
+    // in mtrick mode the M = 128 descriptor walks 128 / chunky chunk slots past the dy buffers: keep that inside the stage
+    if (w.mtrick && (128 / w.chunky) * w.rows_y * w.swy > stage_bytes(w.CB, 1)) return w;
+    w.groups = ceil_div(w.ncb_total, w.CB);
+    w.ok = true;
+    return w;
+}
+
+bool conv_tc_wgrad_supported(const ConvGeom &g) { return make_wg_plan(g).ok && tmap_encode_fn() != nullptr; }
+
+static size_t wg_align(size_t v) { return (v + 1023) / 1024 * 1024; }
+
+size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
+    const WgPlan w = make_wg_plan(g);
+    if (!w.ok) return 0;
+    const int planes = precision == 1 ? 1 : 2;
+    const size_t rows_y = (size_t)g.n * g.od * g.oh * g.ow, rows_x = (size_t)g.n * g.d * g.h * g.w;
+    return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + 2048;
+}
+
+int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    const WgPlan w = make_wg_plan(g);
+    if (!w.ok) return MDT_EUNSUPPORTED;
+    if (ws_bytes < conv_tc_wgrad_workspace_bytes(g, precision)) return MDT_EWORKSPACE;
+    const int planes = precision == 1 ? 1 : 2;
+    const int T = g.kd * g.kh * g.kw;
+    const long long rows_y = (long long)g.n * g.od * g.oh * g.ow, rows_x = (long long)g.n * g.d * g.h * g.w;
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    __nv_bfloat16 *ys = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2));
+    auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp) {
+        long long blocks = ceil_div<long long>(rows * (Cp / 8), 256);
+        if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, C, Cp, planes);
+        return launch_status();
+    };
+    int rc = split(dy, ys, rows_y, g.cout, w.co_p);
+    if (rc) return rc;
+    if ((rc = split(x, xs, rows_x, g.cin, w.ci_p))) return rc;
+    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * T, st);
+    if (e != cudaSuccess) return (int)e;
+
+    TcWgradParams p{};
+    p.NB = g.n; p.OD = g.od; p.OH = g.oh; p.OW = g.ow; p.D = g.d; p.H = g.h; p.W = g.w;
+    p.KD = g.kd; p.KH = g.kh; p.KW = g.kw; p.sd = g.sd; p.sh = g.sh; p.pd = g.pd; p.ph = g.ph; p.pw = g.pw;
+    p.cin = g.cin; p.cout = g.cout; p.T = T;
+    p.seg = w.seg; p.segs = w.segs; p.ksteps = w.ksteps;
+    p.swy = w.swy; p.chunky = w.chunky; p.nmc = w.nmc; p.co_p = w.co_p; p.mtrick = w.mtrick;
+    p.swx = w.swx; p.chunkx = w.chunkx; p.nxc = w.nxc;
+    p.ncb_total = w.ncb_total; p.CB = w.CB; p.groups = w.groups;
+    p.planes = planes;
+    p.y_chunk_bytes = w.rows_y * w.swy;
+    p.y_plane_bytes = w.nmc * p.y_chunk_bytes;
+    p.x_plane_bytes = w.rows_x_pad * w.swx;
+    p.x_buf_bytes = planes * p.x_plane_bytes;
+    p.stage_bytes = (int)wg_align((size_t)planes * p.y_plane_bytes + (size_t)w.CB * p.x_buf_bytes);
+    p.y_tx_bytes = w.rows_y * w.swy;
+    p.x_tx_bytes = w.rows_x * w.swx;
+    p.units = (long long)g.n * g.od * g.oh * w.segs;
+    p.dw = dw;
+    long long splits = ceil_div<long long>((long long)num_sms() * 2, (long long)w.groups * w.mtiles);
+    if (splits < 1) splits = 1;
+    if (splits > p.units) splits = p.units;
+    p.splits = (int)splits;
+
+    CUtensorMap tmY, tmX;
+    {
+        const uint64_t dims[5] = {(uint64_t)w.co_p, (uint64_t)g.ow, (uint64_t)g.oh, (uint64_t)g.od, (uint64_t)g.n * planes};
+        const uint64_t str[4] = {(uint64_t)w.co_p * 2, (uint64_t)g.ow * w.co_p * 2, (uint64_t)g.oh * g.ow * w.co_p * 2,
+                                 (uint64_t)g.od * g.oh * g.ow * w.co_p * 2};
+        const uint32_t box[5] = {(uint32_t)w.chunky, (uint32_t)w.rows_y, 1u, 1u, 1u};
+        if (!encode_bf16_tmap(&tmY, ys, 5, dims, str, box, w.swy)) return MDT_EDRIVER;
+        const uint64_t xd[5] = {(uint64_t)w.ci_p, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.d, (uint64_t)g.n * planes};
+        const uint64_t xs_[4] = {(uint64_t)w.ci_p * 2, (uint64_t)g.w * w.ci_p * 2, (uint64_t)g.h * g.w * w.ci_p * 2,
+                                 (uint64_t)g.d * g.h * g.w * w.ci_p * 2};
+        const uint32_t xbox[5] = {(uint32_t)w.chunkx, (uint32_t)w.rows_x, 1u, 1u, 1u};
+        if (!encode_bf16_tmap(&tmX, xs, 5, xd, xs_, xbox, w.swx)) return MDT_EDRIVER;
+    }
+    const size_t smem = (size_t)kWgStages * p.stage_bytes + 1024;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER;
+        attr = true;
+    }
+    dim3 grid((unsigned)(w.groups * p.splits), w.mtiles);
+    conv_tc_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(tmY, tmX, p);
+    if ((rc = launch_status())) return rc;
+    if (db) return conv_bias_grad(g, dy, db, st);
+    return MDT_OK;
+}
+
+}  // namespace mdt
