@@ -170,7 +170,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         const int m = q * 32 + lane;   // TMEM lane = row of D
         // which cout does this lane hold?  mtrick: lanes [0, co_p) = hi part, [co_p, 2 co_p) = lo part (same cout), rest unused
         int co = -1;
-        if (p.mtrick) { if (m < 2 * p.co_p) co = m % p.co_p; }
+        if (p.mtrick) { if (m < (p.planes > 1 ? 2 : 1) * p.co_p) co = m % p.co_p; }   // single-plane mode has no lo half
         else co = mt * 128 + m;
         const bool co_ok = co >= 0 && co < p.cout;
         for (int b = 0; b < ncb; ++b) {

@@ -1,0 +1,56 @@
+"""N > 1 host logic on CPU: world_size-2 gloo run of the flat-gradient all-reduce (the only exchange step of the data-parallel path)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from medicaldetectiontoolkit_b200.parallel import FlatGradAllReduce
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.ReLU(), torch.nn.Linear(3, 2))
+    unused = torch.nn.Parameter(torch.ones(5))   # a parameter that never receives a gradient (like Fpn.P1_conv2.*)
+    net.register_parameter("unused", unused)
+    red = FlatGradAllReduce(net, world)
+    x = torch.full((2, 4), float(rank + 1))
+    red.zero_grad()
+    net(x).sum().backward()
+    local = red.flat.clone()
+    red.all_reduce()
+    off_unused = [o for p, o in _offsets(red) if p is unused][0]
+    q.put((rank, local, red.flat.clone(), [p.grad.data_ptr() == red.flat[o:o + p.numel()].data_ptr() for p, o in _offsets(red)], off_unused))
+    dist.destroy_process_group()
+
+
+def _offsets(red):
+    off = 0
+    for p in red.params:
+        yield p, off
+        off += p.numel()
+
+
+def test_flat_grad_allreduce_gloo_world2():
+    world, port = 2, 29611
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    mean = (out[0][1] + out[1][1]) / 2
+    for rank, local, reduced, views, off_unused in out:
+        assert torch.allclose(reduced, mean)          # averaged gradients on every rank
+        assert all(views)                             # .grad tensors are views of the flat buffer (no flatten copies)
+        assert torch.all(reduced[off_unused:off_unused + 5] == 0)   # never-used parameter stays zero: static bucket layout
+    assert not torch.allclose(out[0][1], out[1][1])   # ranks really had different local gradients
