@@ -210,7 +210,7 @@ def main():
     conv_ms = None
     if C.EVENT_LOG is not None:
         torch.cuda.synchronize()
-        conv_ms = sum(a.elapsed_time(b) for a, b in C.EVENT_LOG) / args.steps
+        conv_ms = sum(a.elapsed_time(b) for a, b, _ in C.EVENT_LOG) / args.steps
         n_conv_calls = len(C.EVENT_LOG) / args.steps
     C.EVENT_LOG = None
     # --- end to end through the public API with host buffers

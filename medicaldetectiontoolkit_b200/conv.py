@@ -46,11 +46,11 @@ def _ev_start():
     return e
 
 
-def _ev_end(e0):
+def _ev_end(e0, tag=None):
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        EVENT_LOG.append((e0, e1))
+        EVENT_LOG.append((e0, e1, tag))
 
 
 def _desc(x_shape, w_shape, stride, padding, relu, precision, algo):
@@ -84,7 +84,7 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
     with torch.cuda.device(x.device):
         ev = _ev_start()
         L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev)
+        _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), lib.mdt_conv3d_algo(d, 0)))
     return y
 
 
@@ -100,7 +100,7 @@ def conv3d_dgrad(dy, weight, x_shape, stride, padding, precision=None, algo=None
     with torch.cuda.device(dy.device):
         ev = _ev_start()
         L.check(lib.mdt_conv3d_dgrad(d, L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev)
+        _ev_end(ev, (1, tuple(x_shape), tuple(w.shape), tuple(stride), lib.mdt_conv3d_algo(d, 1)))
     return dx
 
 
@@ -117,7 +117,7 @@ def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, alg
     with torch.cuda.device(x.device):
         ev = _ev_start()
         L.check(lib.mdt_conv3d_wgrad(d, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev)
+        _ev_end(ev, (2, tuple(x.shape), tuple(w_shape), tuple(stride), lib.mdt_conv3d_algo(d, 2)))
     return dw, db
 
 

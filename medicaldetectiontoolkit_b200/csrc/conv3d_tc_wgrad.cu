@@ -243,8 +243,6 @@ static WgPlan make_wg_plan(const ConvGeom &g) {
     auto stage_bytes = [&](int cb, int planes) { return planes * w.nmc * w.rows_y * w.swy + cb * planes * w.rows_x_pad * w.swx; };
     while (w.CB > 1 && kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) --w.CB;
     if (kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) return w;
-    // in mtrick mode the M = 128 descriptor walks 128 / chunky chunk slots past the dy buffers: keep that inside the stage
-    if (w.mtrick && (128 / w.chunky) * w.rows_y * w.swy > stage_bytes(w.CB, 1)) return w;
     w.groups = ceil_div(w.ncb_total, w.CB);
     w.ok = true;
     return w;
@@ -321,7 +319,12 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
         const uint32_t xbox[5] = {(uint32_t)w.chunkx, (uint32_t)w.rows_x, 1u, 1u, 1u};
         if (!encode_bf16_tmap(&tmX, xs, 5, xd, xs_, xbox, w.swx)) return MDT_EDRIVER;
     }
-    const size_t smem = (size_t)kWgStages * p.stage_bytes + 1024;
+    // the M = 128 dy descriptor walks 128 / chunky chunk slots from the stage base (rows past the real dy chunks are ignored by the
+    // epilogue); make sure that walk stays inside the allocation for the last stage too
+    const size_t walk = (size_t)(128 / w.chunky) * w.rows_y * w.swy;
+    const size_t tail = walk > (size_t)p.stage_bytes ? walk - p.stage_bytes : 0;
+    const size_t smem = (size_t)kWgStages * p.stage_bytes + 1024 + tail;
+    if (smem > 218 * 1024) return MDT_EUNSUPPORTED;
     static bool attr = false;
     if (!attr) {
         if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER;

@@ -233,3 +233,33 @@ def unique1d(tensor):
     if tensor.numel() < 2:
         return tensor
     return torch.unique(tensor, sorted=True)
+
+
+def bbox_overlaps(boxes1, boxes2):
+    """IoU matrix [n1, n2] of two box sets on the device, no +1 extents (utils/model_utils.py:430-501 bbox_overlaps_{2D,3D}),
+    by broadcasting instead of the reference's repeat/tile copies; same operation order per pair: (dx*dy)[*dz], v1 + v2 - inter."""
+    dim = boxes1.shape[1] // 2
+    a, b = boxes1.unsqueeze(1), boxes2.unsqueeze(0)
+    dy = (torch.min(a[..., 2], b[..., 2]) - torch.max(a[..., 0], b[..., 0])).clamp_min(0)
+    dx = (torch.min(a[..., 3], b[..., 3]) - torch.max(a[..., 1], b[..., 1])).clamp_min(0)
+    inter = dx * dy
+    v1 = (a[..., 2] - a[..., 0]) * (a[..., 3] - a[..., 1])
+    v2 = (b[..., 2] - b[..., 0]) * (b[..., 3] - b[..., 1])
+    if dim == 3:
+        inter = inter * (torch.min(a[..., 5], b[..., 5]) - torch.max(a[..., 4], b[..., 4])).clamp_min(0)
+        v1 = v1 * (a[..., 5] - a[..., 4])
+        v2 = v2 * (b[..., 5] - b[..., 4])
+    return inter / (v1 + v2 - inter)
+
+
+bbox_overlaps_2D = bbox_overlaps
+bbox_overlaps_3D = bbox_overlaps
+
+
+def shem(roi_probs_neg, negative_count, ohem_poolsize):
+    """stochastic hard example mining (utils/model_utils.py:674-691): sample `negative_count` indices out of the
+    `negative_count * ohem_poolsize` highest-scoring (max foreground probability) candidates; device randperm."""
+    probs, order = roi_probs_neg[:, 1:].max(1)[0].sort(descending=True)
+    select = min(ohem_poolsize * int(negative_count), order.shape[0])
+    pool = order[:select]
+    return pool[torch.randperm(pool.shape[0], device=pool.device)[:negative_count]]

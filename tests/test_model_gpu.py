@@ -105,3 +105,51 @@ def test_retina_losses_match_reference_formulas():
     assert abs(bl.item() - want.item()) < 1e-6
     none = torch.full((A,), -1, dtype=torch.int32, device=DEV)
     assert compute_bbox_loss(tgt, deltas, none, max_pos=3).item() == 0.0
+
+
+def test_mrcnn_train_step_small():
+    """cfg3-style two-stage model end to end: proposals (NMS 0.7) -> RoIAlign (7,7,3)/(14,14,5) -> heads -> detection targets incl. RoIAlign
+    (28,28,10) on GT masks -> 5 losses -> backward through RoIAlign into the FPN"""
+    from medicaldetectiontoolkit_b200 import mrcnn
+    cf = make_cf('mrcnn', 3, (64, 64, 32))
+    cf.post_nms_rois_training = 64
+    cf.post_nms_rois_inference = 64
+    cf.pre_nms_limit = 1000
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = mrcnn.net(cf, None).to(DEV)
+    keys = set(net.state_dict().keys())
+    for k in ['fpn.C1.0.weight', 'fpn.C2.1.conv1.0.weight', 'fpn.P5_conv1.bias', 'rpn.conv_shared.0.weight', 'rpn.conv_class.weight', 'rpn.conv_bbox.bias',
+              'classifier.conv1.0.weight', 'classifier.linear_class.weight', 'classifier.linear_bbox.bias', 'mask.conv4.0.bias',
+              'mask.deconv.weight', 'mask.deconv.bias', 'mask.conv5.weight']:
+        assert k in keys, k
+    assert tuple(net.mask.deconv.weight.shape) == (36, 36, 2, 2, 2) and tuple(net.classifier.conv1[0].weight.shape) == (144, 36, 7, 7, 3)
+    batch = synthetic_batch(cf, 2, seed=2, with_masks=True)
+    res = net.train_forward(batch)
+    assert res['seg_preds'].shape == (2, 1, 64, 64, 32)
+    loss = res['torch_loss']
+    assert torch.isfinite(loss).all()
+    loss.backward()
+    g = {k: p.grad for k, p in net.named_parameters()}
+    assert g['rpn.conv_shared.0.weight'] is not None and torch.isfinite(g['rpn.conv_shared.0.weight']).all()
+    assert g['classifier.conv1.0.weight'] is not None and g['mask.deconv.weight'] is not None
+    assert g['fpn.C1.0.weight'].abs().sum() > 0          # gradients reach the stem through RoIAlign backward
+    out = net.test_forward({'data': batch['data']}, return_masks=True)
+    assert out['seg_preds'].shape == (2, 1, 64, 64, 32)
+
+
+def test_deconv2x_matches_conv_transpose():
+    from medicaldetectiontoolkit_b200.mrcnn import _Deconv2x
+    torch.manual_seed(1)
+    m = _Deconv2x(36, 36, 3).to(DEV)
+    x = torch.randn(3, 36, 5, 6, 4, device=DEV, requires_grad=True)
+    y = m(x)
+    xr = x.detach().double().requires_grad_(True)
+    yr = torch.nn.functional.conv_transpose3d(xr, m.weight.double(), m.bias.double(), stride=2)
+    assert _rel(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 1e-4
+    g = torch.randn_like(y)
+    y.backward(g)
+    yr.backward(g.double())
+    assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
+
+    assert m.weight.grad is not None and torch.isfinite(m.weight.grad).all()
