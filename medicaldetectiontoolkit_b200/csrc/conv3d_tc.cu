@@ -316,7 +316,6 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     const bool dgrad = pass == 1;
     pl.Kc = dgrad ? g.cout : g.cin;
     pl.Nc = dgrad ? g.cin : g.cout;
-    if (pl.Kc < 8) return pl;            // Cin = 1 stem etc.: bandwidth-bound direct kernel
     pl.RD = dgrad ? g.d : g.od; pl.RH = dgrad ? g.h : g.oh; pl.RW = dgrad ? g.w : g.ow;
     pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
     pl.Kp = ceil_div(pl.Kc, 16) * 16;

@@ -209,7 +209,6 @@ struct WgPlan {
 static WgPlan make_wg_plan(const ConvGeom &g) {
     WgPlan w;
     if (g.sw != 1) return w;
-    if (g.cin < 8 || g.cout < 8) return w;
     // x (N side): one chunk spans all of ci when ci <= 64, so that all kw taps of a pair fit one MMA
     w.ci_p = g.cin <= 16 ? 16 : g.cin <= 32 ? 32 : ceil_div(g.cin, 64) * 64;
     w.chunkx = w.ci_p < 64 ? w.ci_p : 64;
