@@ -52,8 +52,10 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
 // weights [Cout, Cin, T] fp32 -> bf16 planes [planes][T][Nrows][Kp]  (K contiguous)
 //   mode 0 (fprop): Nrows = Cout (padded Np), K = Cin:  B[t][co][ci] = w[co][ci][t]
 //   mode 1 (dgrad): Nrows = Cin  (padded Np), K = Cout: B[t][ci][co] = w[co][ci][t]
+// The packed tensor is written `reps` times: every CTA of the conv kernel streams the SAME weight tiles at about the same time, and a
+// single copy makes all SMs hit the same few L2 slices in lockstep; CTAs pick replica blockIdx.x % reps, spreading the load.
 __global__ void __launch_bounds__(256) pack_weights_tc_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ dst, int cout, int cin, int T,
-                                                             int Np, int Kp, int planes, int mode) {
+                                                             int Np, int Kp, int planes, int mode, int reps) {
     const long long total = (long long)T * Np * Kp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i % Kp);
@@ -63,8 +65,11 @@ __global__ void __launch_bounds__(256) pack_weights_tc_kernel(const float *__res
         if (mode == 0) { if (n < cout && k < cin) v = w[((size_t)n * cin + k) * T + t]; }
         else           { if (n < cin && k < cout) v = w[((size_t)k * cin + n) * T + t]; }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        dst[i] = hi;
-        if (planes > 1) dst[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+        for (int r = 0; r < reps; ++r) {
+            dst[(size_t)r * planes * total + i] = hi;
+            if (planes > 1) dst[(size_t)r * planes * total + total + i] = lo;
+        }
     }
 }
 
@@ -84,6 +89,7 @@ struct TcConvParams {
     int DA, DB;           // ring depths
     int a_slot_bytes, b_slot_bytes, a_plane_bytes, b_plane_bytes, a_tx_bytes;
     int relu;
+    int wreps;            // weight replicas in global memory
     const float *bias, *residual;
     float *out;
 };
@@ -191,9 +197,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_wait(&emptyB[s], ((itB / p.DB) & 1) ^ 1);
                             mbar_arrive_expect_tx(&fullB[s], p.planes * p.b_plane_bytes);
                             const int tap = (kd * p.KH + kh) * p.KW + kw;
+                            const int rep = blockIdx.x % p.wreps;
                             for (int pl = 0; pl < p.planes; ++pl)
                                 tma_load_3d(sB + (size_t)s * p.b_slot_bytes + (size_t)pl * p.b_plane_bytes, &tmB, &fullB[s], c * chunk_elems, n0,
-                                            tap + pl * T);
+                                            tap + (rep * p.planes + pl) * T);
                             ++itB;
                         }
                     }
@@ -352,13 +359,20 @@ bool conv_tc_supported(const ConvGeom &g, int pass) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// number of weight replicas: as many as fit in ~16 MB, at most 16
+static int weight_reps(const TcPlan &pl, int T, int planes) {
+    const size_t one = (size_t)planes * T * pl.Np * pl.Kp * 2;
+    int r = (int)((16u << 20) / (one ? one : 1));
+    return r < 1 ? 1 : r > 16 ? 16 : r;
+}
+
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
     if (pass == 2) return conv_tc_wgrad_workspace_bytes(g, precision);
     const TcPlan pl = make_plan(g, pass);
     if (!pl.ok) return 0;
     const int planes = precision == 1 ? 1 : 2;
     const int T = g.kd * g.kh * g.kw;
-    return align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024) + align_up((size_t)planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
+    return align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024) + align_up((size_t)weight_reps(pl, T, planes) * planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
 }
 
 static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
@@ -381,7 +395,8 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
         int rc = launch_status();
         if (rc) return rc;
         const long long wt = (long long)T * pl.Np * pl.Kp;
-        pack_weights_tc_kernel<<<(unsigned)ceil_div<long long>(wt, 256), 256, 0, st>>>(w, wp, g.cout, g.cin, T, pl.Np, pl.Kp, planes, dgrad ? 1 : 0);
+        pack_weights_tc_kernel<<<(unsigned)ceil_div<long long>(wt, 256), 256, 0, st>>>(w, wp, g.cout, g.cin, T, pl.Np, pl.Kp, planes, dgrad ? 1 : 0,
+                                                                                      weight_reps(pl, T, planes));
         if ((rc = launch_status())) return rc;
     }
 
@@ -406,6 +421,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DB > 2) --p.DB;
     if (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget) return MDT_EUNSUPPORTED;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
+    p.wreps = weight_reps(pl, T, planes);
 
     // tensor maps.  A: bf16 [planes*N][SD][SH][SW][Kp];  B: bf16 [planes*T][Np][Kp]
     CUtensorMap tmA, tmB;
@@ -415,7 +431,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
                                      (uint64_t)pl.SD * pl.SH * pl.SW * pl.Kp * 2};
         const uint32_t box[5] = {(uint32_t)(pl.swz / 2), (uint32_t)(pl.halo ? a_rows_loaded : pl.BW), (uint32_t)pl.BH, 1u, 1u};
         if (!encode_bf16_tmap(&tmA, xs, 5, dims, strides, box, pl.swz)) return MDT_EDRIVER;
-        const uint64_t bdims[3] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)T * planes};
+        const uint64_t bdims[3] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)T * planes * p.wreps};
         const uint64_t bstr[2] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.Np * pl.Kp * 2};
         const uint32_t bbox[3] = {(uint32_t)(pl.swz / 2), (uint32_t)pl.NT, 1u};
         if (!encode_bf16_tmap(&tmB, wp, 3, bdims, bstr, bbox, pl.swz)) return MDT_EDRIVER;

@@ -34,7 +34,8 @@ struct TcWgradParams {
     int y_chunk_bytes, y_plane_bytes, x_plane_bytes, x_buf_bytes, stage_bytes;
     int y_tx_bytes, x_tx_bytes;      // bytes one TMA box delivers
     long long units;                 // NB * OD * OH * segs
-    float *dw;
+    float *partial;                  // [split][group][mtile][128 lanes][512 cols] fp32 accumulator dumps (reduced by wgrad_reduce_kernel)
+    int mtiles;
 };
 
 constexpr int kWgThreads = 192;
@@ -163,38 +164,60 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         }
     }
     if (warp >= 2) {
+        // epilogue: dump this CTA's accumulators (TMEM lanes x used columns) to its slot of the partial buffer — plain coalesced-ish
+        // stores, no atomics; the cross-CTA (split-K) reduction is a separate streaming kernel
         mbar_wait(&accum_full, 0);
         tc_fence_after();
         const uint32_t started = *(volatile uint32_t *)&s_started;
         const int q = warp & 3;
-        const int m = q * 32 + lane;   // TMEM lane = row of D
-        // which cout does this lane hold?  mtrick: lanes [0, co_p) = hi part, [co_p, 2 co_p) = lo part (same cout), rest unused
-        int co = -1;
-        if (p.mtrick) { if (m < (p.planes > 1 ? 2 : 1) * p.co_p) co = m % p.co_p; }   // single-plane mode has no lo half
-        else co = mt * 128 + m;
-        const bool co_ok = co >= 0 && co < p.cout;
+        const int m = q * 32 + lane;
+        float *slot = p.partial + (((size_t)split * p.groups + group) * p.mtiles + mt) * (size_t)(128 * 512) + (size_t)m * 512;
         for (int b = 0; b < ncb; ++b) {
-            if (!((started >> b) & 1u)) continue;
-            int kd, kh, xc;
-            wg_decode_cb(p, cb0 + b, kd, kh, xc);
+            const bool live = (started >> b) & 1u;
             for (int c0 = 0; c0 < ncols; c0 += 16) {
                 float v[16];
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * ncols + c0, v);
-                tmem_ld_wait();
-                if (!co_ok) continue;
+                if (live) {
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + b * ncols + c0, v);
+                    tmem_ld_wait();
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = c0 + j;
-                    const int kw = col / p.chunkx, ci = xc * p.chunkx + col % p.chunkx;
-                    if (ci < p.cin && v[j] != 0.f)
-                        atomicAdd(p.dw + ((size_t)co * p.cin + ci) * p.T + (kd * p.KH + kh) * p.KW + kw, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
                 }
+                float4 *dst = reinterpret_cast<float4 *>(slot + b * ncols + c0);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                dst[2] = make_float4(v[8], v[9], v[10], v[11]);
+                dst[3] = make_float4(v[12], v[13], v[14], v[15]);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// dw[co, ci, tap] = sum over splits (and over the hi / lo lane halves in mtrick mode) of the partial accumulators
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(TcWgradParams p, float *__restrict__ dw) {
+    const int ncols = p.KW * p.chunkx;
+    const long long total = (long long)p.cout * p.ncb_total * ncols;     // (co, column block, col)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % ncols);
+        const int cb = (int)((i / ncols) % p.ncb_total);
+        const int co = (int)(i / ((long long)ncols * p.ncb_total));
+        int kd, kh, xc;
+        wg_decode_cb(p, cb, kd, kh, xc);
+        const int kw = col / p.chunkx, ci = xc * p.chunkx + col % p.chunkx;
+        if (ci >= p.cin) continue;
+        const int group = cb / p.CB, b = cb % p.CB;
+        const int mt = p.mtrick ? 0 : co / 128, m = p.mtrick ? co : co % 128;
+        float acc = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+            const float *slot = p.partial + (((size_t)sp * p.groups + group) * p.mtiles + mt) * (size_t)(128 * 512) + b * ncols + col;
+            acc += slot[(size_t)m * 512];
+            if (p.mtrick && p.planes > 1) acc += slot[(size_t)(m + p.co_p) * 512];
+        }
+        dw[((size_t)co * p.cin + ci) * p.T + (kd * p.KH + kh) * p.KW + kw] = acc;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -251,12 +274,22 @@ bool conv_tc_wgrad_supported(const ConvGeom &g) { return make_wg_plan(g).ok && t
 
 static size_t wg_align(size_t v) { return (v + 1023) / 1024 * 1024; }
 
+// split-K factor: one full wave of CTAs (1 CTA per SM: the kernel uses most of the shared memory)
+static int wg_splits(const ConvGeom &g, const WgPlan &w) {
+    const long long units = (long long)g.n * g.od * g.oh * w.segs;
+    long long splits = (long long)num_sms() / ((long long)w.groups * w.mtiles);
+    if (splits < 1) splits = 1;
+    if (splits > units) splits = units;
+    return (int)splits;
+}
+
 size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
     const WgPlan w = make_wg_plan(g);
     if (!w.ok) return 0;
     const int planes = precision == 1 ? 1 : 2;
     const size_t rows_y = (size_t)g.n * g.od * g.oh * g.ow, rows_x = (size_t)g.n * g.d * g.h * g.w;
-    return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + 2048;
+    const size_t partial = (size_t)wg_splits(g, w) * w.groups * w.mtiles * 128 * 512 * sizeof(float);
+    return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + wg_align(partial) + 2048;
 }
 
 int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
@@ -279,8 +312,6 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     int rc = split(dy, ys, rows_y, g.cout, w.co_p);
     if (rc) return rc;
     if ((rc = split(x, xs, rows_x, g.cin, w.ci_p))) return rc;
-    cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g.cout * g.cin * T, st);
-    if (e != cudaSuccess) return (int)e;
 
     TcWgradParams p{};
     p.NB = g.n; p.OD = g.od; p.OH = g.oh; p.OW = g.ow; p.D = g.d; p.H = g.h; p.W = g.w;
@@ -299,11 +330,9 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     p.y_tx_bytes = w.rows_y * w.swy;
     p.x_tx_bytes = w.rows_x * w.swx;
     p.units = (long long)g.n * g.od * g.oh * w.segs;
-    p.dw = dw;
-    long long splits = ceil_div<long long>((long long)num_sms() * 2, (long long)w.groups * w.mtiles);
-    if (splits < 1) splits = 1;
-    if (splits > p.units) splits = p.units;
-    p.splits = (int)splits;
+    p.splits = wg_splits(g, w);
+    p.mtiles = w.mtiles;
+    p.partial = reinterpret_cast<float *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2) + wg_align((size_t)planes * rows_x * w.ci_p * 2));
 
     CUtensorMap tmY, tmX;
     {
@@ -332,6 +361,11 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     dim3 grid((unsigned)(w.groups * p.splits), w.mtiles);
     conv_tc_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(tmY, tmX, p);
     if ((rc = launch_status())) return rc;
+    {
+        const long long total = (long long)g.cout * w.ncb_total * g.kw * w.chunkx;
+        wgrad_reduce_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(p, dw);
+        if ((rc = launch_status())) return rc;
+    }
     if (db) return conv_bias_grad(g, dy, db, st);
     return MDT_OK;
 }
