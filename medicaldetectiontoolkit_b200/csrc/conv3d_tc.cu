@@ -86,8 +86,8 @@ struct TcConvParams {
     int planes;           // 1 = bf16, 2 = split-bf16 x3
     int BW, BH, halo;     // tile = BH lines x BW voxels = 128 rows; halo mode iff BH == 1
     int tiles_w, tiles_h;
-    int DA, DB;           // ring depths
-    int a_slot_bytes, b_slot_bytes, a_plane_bytes, b_plane_bytes, a_tx_bytes;
+    int CPS, TPS, D;      // K chunks per stage, taps per stage (KW in halo mode, 1 otherwise), ring depth
+    int a_plane_bytes, b_plane_bytes, a_tx_bytes, stage_bytes, a_region_bytes;
     int relu;
     int wreps;            // weight replicas in global memory
     const float *bias, *residual;
@@ -95,6 +95,7 @@ struct TcConvParams {
 };
 
 constexpr int kTcThreads = 192;
+constexpr int kTcMaxStages = 6;
 
 // source line (d_src, h_src) feeding tile row-line (rd, rh0) through tap (kd, kh); false = this tap contributes nothing to the tile
 __device__ __forceinline__ bool tc_step_coords(const TcConvParams &p, int rd, int rh0, int kd, int kh, int &d_src, int &h_src) {
@@ -118,20 +119,21 @@ __device__ __forceinline__ bool tc_step_coords(const TcConvParams &p, int rd, in
     return true;
 }
 
+// Pipeline stage = one (kd, kh) x a group of CPS K-chunks: the A halo line(s) of those chunks + the B tiles of the TPS taps sharing it.
+// One full / one empty mbarrier per stage; the MMA thread waits once, issues TPS * CPS * (swz/32) * {1|2} MMAs back to back, commits once.
+// Split-bf16 uses N-stacking: the hi and lo weight planes of a tile are adjacent in shared memory, so  A_hi x [B_hi ; B_lo]  is ONE
+// MMA with N = 2*NT (accumulator columns [0,NT) += hi*hi, [NT,2NT) += hi*lo) followed by  A_lo x B_hi  (N = NT); the epilogue adds the
+// two column halves.  2 MMAs and 2 A reads per K step instead of 3.
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t fullA[4], emptyA[4], fullB[8], emptyB[8], accum_full;
+    __shared__ uint64_t full[kTcMaxStages], empty[kTcMaxStages], accum_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_have_acc;
     __shared__ float s_bias[128];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *sA = smem;
-    uint8_t *sB = smem + (size_t)p.DA * p.a_slot_bytes;
-
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // tile decode: blockIdx.x -> (n, rd, tile_h, tile_w); blockIdx.y -> N tile
     int t = blockIdx.x;
     const int tw = t % p.tiles_w; t /= p.tiles_w;
     const int th = t % p.tiles_h; t /= p.tiles_h;
@@ -141,22 +143,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n0 = blockIdx.y * p.NT;
     const int T = p.KD * p.KH * p.KW;
     const int chunk_elems = p.swz >> 1;
+    const int ngroups = (p.nchunks + p.CPS - 1) / p.CPS;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.DA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-        for (int i = 0; i < p.DB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < p.D; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&accum_full, 1);
         s_have_acc = 1;
         fence_barrier_init();
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + 128) {
+    if (threadIdx.x >= 64) {
         const int c = threadIdx.x - 64;
         s_bias[c] = (p.bias && n0 + c < p.Cn) ? __ldg(p.bias + n0 + c) : 0.f;
     }
+    const int acc_cols = p.planes > 1 ? 2 * p.NT : p.NT;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < p.NT) tmem_cols <<= 1;
+    while ((int)tmem_cols < acc_cols) tmem_cols <<= 1;
     if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -166,42 +169,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // =============================================================== TMA producer
         if (lane == 0) {
-            int itA = 0, itB = 0;
+            int s = 0;
+            uint32_t ph = 1;   // parity to wait for on `empty` (fresh barrier: the "previous" phase counts as complete)
+            const int rep = blockIdx.x % p.wreps;
             for (int kd = 0; kd < p.KD; ++kd)
                 for (int kh = 0; kh < p.KH; ++kh) {
                     int d_src, h_src;
                     if (!tc_step_coords(p, rd, rh0, kd, kh, d_src, h_src)) continue;
-                    for (int c = 0; c < p.nchunks; ++c) {
-                        if (p.halo) {
-                            const int s = itA % p.DA;
-                            mbar_wait(&emptyA[s], ((itA / p.DA) & 1) ^ 1);
-                            mbar_arrive_expect_tx(&fullA[s], p.planes * p.a_tx_bytes);
-                            const int w_start = p.dgrad ? rw0 + p.pw - (p.KW - 1) : rw0 - p.pw;
-                            for (int pl = 0; pl < p.planes; ++pl)
-                                tma_load_5d(sA + (size_t)s * p.a_slot_bytes + (size_t)pl * p.a_plane_bytes, &tmA, &fullA[s], c * chunk_elems, w_start,
-                                            h_src, d_src, nb + pl * p.NB);
-                            ++itA;
-                        }
-                        for (int kw = 0; kw < p.KW; ++kw) {
-                            if (!p.halo) {
-                                const int s = itA % p.DA;
-                                mbar_wait(&emptyA[s], ((itA / p.DA) & 1) ^ 1);
-                                mbar_arrive_expect_tx(&fullA[s], p.planes * p.a_tx_bytes);
-                                const int w_start = p.dgrad ? rw0 + p.pw - kw : rw0 - p.pw + kw;
+                    for (int g = 0; g < ngroups; ++g) {
+                        const int c_lo = g * p.CPS, cn = min(p.CPS, p.nchunks - c_lo);
+                        for (int kw0 = 0; kw0 < p.KW; kw0 += p.TPS) {
+                            mbar_wait(&empty[s], ph);
+                            uint8_t *st = smem + (size_t)s * p.stage_bytes;
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)(cn * p.planes * (p.a_tx_bytes + p.TPS * p.b_plane_bytes)));
+                            int w_start;
+                            if (p.halo) w_start = p.dgrad ? rw0 + p.pw - (p.KW - 1) : rw0 - p.pw;
+                            else        w_start = p.dgrad ? rw0 + p.pw - kw0 : rw0 - p.pw + kw0;
+                            for (int c = 0; c < cn; ++c)
                                 for (int pl = 0; pl < p.planes; ++pl)
-                                    tma_load_5d(sA + (size_t)s * p.a_slot_bytes + (size_t)pl * p.a_plane_bytes, &tmA, &fullA[s], c * chunk_elems,
-                                                w_start, h_src, d_src, nb + pl * p.NB);
-                                ++itA;
+                                    tma_load_5d(st + (size_t)(c * p.planes + pl) * p.a_plane_bytes, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start,
+                                                h_src, d_src, nb + pl * p.NB);
+                            uint8_t *sb = st + p.a_region_bytes;
+                            for (int k = 0; k < p.TPS; ++k) {
+                                const int tap = (kd * p.KH + kh) * p.KW + kw0 + k;
+                                for (int c = 0; c < cn; ++c)
+                                    for (int pl = 0; pl < p.planes; ++pl)
+                                        tma_load_3d(sb + (size_t)((k * p.CPS + c) * p.planes + pl) * p.b_plane_bytes, &tmB, &full[s],
+                                                    (c_lo + c) * chunk_elems, n0, tap + (rep * p.planes + pl) * T);
                             }
-                            const int s = itB % p.DB;
-                            mbar_wait(&emptyB[s], ((itB / p.DB) & 1) ^ 1);
-                            mbar_arrive_expect_tx(&fullB[s], p.planes * p.b_plane_bytes);
-                            const int tap = (kd * p.KH + kh) * p.KW + kw;
-                            const int rep = blockIdx.x % p.wreps;
-                            for (int pl = 0; pl < p.planes; ++pl)
-                                tma_load_3d(sB + (size_t)s * p.b_slot_bytes + (size_t)pl * p.b_plane_bytes, &tmB, &fullB[s], c * chunk_elems, n0,
-                                            tap + (rep * p.planes + pl) * T);
-                            ++itB;
+                            if (++s == p.D) { s = 0; ph ^= 1; }
                         }
                     }
                 }
@@ -209,41 +205,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // =============================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
-            const uint32_t lt = layout_type_for_swizzle_bytes(p.swz);
-            const uint32_t sbo = 8u * p.swz;
+            const uint32_t idesc1 = make_idesc_bf16(128, p.NT, 0, 0);
+            const uint32_t idesc2 = make_idesc_bf16(128, 2 * p.NT, 0, 0);
+            // descriptor template: everything but the start address (low 14 bits of the low word)
+            const uint64_t dtmpl = make_smem_desc(0, 16, 8u * p.swz, layout_type_for_swizzle_bytes(p.swz));
             const int ksteps = p.swz / 32;
-            int itA = 0, itB = 0;
+            const uint32_t smem_base = smem_u32(smem);
+            int s = 0;
+            uint32_t ph = 0;
             uint32_t acc = 0;
             for (int kd = 0; kd < p.KD; ++kd)
                 for (int kh = 0; kh < p.KH; ++kh) {
                     int d_src, h_src;
                     if (!tc_step_coords(p, rd, rh0, kd, kh, d_src, h_src)) continue;
-                    for (int c = 0; c < p.nchunks; ++c) {
-                        int sa = itA % p.DA;
-                        if (p.halo) mbar_wait(&fullA[sa], (itA / p.DA) & 1);
-                        for (int kw = 0; kw < p.KW; ++kw) {
-                            if (!p.halo) { sa = itA % p.DA; mbar_wait(&fullA[sa], (itA / p.DA) & 1); }
-                            const int sb = itB % p.DB;
-                            mbar_wait(&fullB[sb], (itB / p.DB) & 1);
+                    for (int g = 0; g < ngroups; ++g) {
+                        const int cn = min(p.CPS, p.nchunks - g * p.CPS);
+                        for (int kw0 = 0; kw0 < p.KW; kw0 += p.TPS) {
+                            mbar_wait(&full[s], ph);
                             tc_fence_after();
-                            const int shift = p.halo ? (p.dgrad ? p.KW - 1 - kw : kw) : 0;
-                            const uint32_t a_hi = smem_u32(sA + (size_t)sa * p.a_slot_bytes) + shift * p.swz;
-                            const uint32_t b_hi = smem_u32(sB + (size_t)sb * p.b_slot_bytes);
-                            for (int j = 0; j < ksteps; ++j) {
-                                const uint64_t da = make_smem_desc(a_hi + j * 32, 16, sbo, lt), db = make_smem_desc(b_hi + j * 32, 16, sbo, lt);
-                                umma_bf16(tmem, da, db, idesc, acc);
-                                acc = 1;
-                                if (p.planes > 1) {
-                                    umma_bf16(tmem, da, make_smem_desc(b_hi + p.b_plane_bytes + j * 32, 16, sbo, lt), idesc, 1);
-                                    umma_bf16(tmem, make_smem_desc(a_hi + p.a_plane_bytes + j * 32, 16, sbo, lt), db, idesc, 1);
+                            const uint32_t st = smem_base + s * p.stage_bytes;
+                            for (int k = 0; k < p.TPS; ++k) {
+                                const int shift = p.halo ? (p.dgrad ? p.KW - 1 - (kw0 + k) : kw0 + k) : 0;
+                                for (int c = 0; c < cn; ++c) {
+                                    const uint32_t a_hi = st + (c * p.planes) * p.a_plane_bytes + shift * p.swz;
+                                    const uint32_t b_hi = st + p.a_region_bytes + ((k * p.CPS + c) * p.planes) * p.b_plane_bytes;
+                                    uint64_t da = dtmpl | (uint64_t)((a_hi >> 4) & 0x3FFF);
+                                    uint64_t db = dtmpl | (uint64_t)((b_hi >> 4) & 0x3FFF);
+                                    uint64_t dal = dtmpl | (uint64_t)(((a_hi + p.a_plane_bytes) >> 4) & 0x3FFF);
+                                    if (p.planes > 1) {
+                                        for (int j = 0; j < ksteps; ++j) {
+                                            umma_bf16(tmem, da, db, idesc2, acc);        // A_hi x [B_hi ; B_lo]
+                                            umma_bf16(tmem, dal, db, idesc1, 1);         // A_lo x B_hi
+                                            acc = 1;
+                                            da += 2; db += 2; dal += 2;                  // +32 bytes along K
+                                        }
+                                    } else {
+                                        for (int j = 0; j < ksteps; ++j) {
+                                            umma_bf16(tmem, da, db, idesc1, acc);
+                                            acc = 1;
+                                            da += 2; db += 2;
+                                        }
+                                    }
                                 }
                             }
-                            umma_commit(&emptyB[sb]);
-                            ++itB;
-                            if (!p.halo) { umma_commit(&emptyA[sa]); ++itA; }
+                            umma_commit(&empty[s]);
+                            if (++s == p.D) { s = 0; ph ^= 1; }
                         }
-                        if (p.halo) { umma_commit(&emptyA[sa]); ++itA; }
                     }
                 }
             if (acc) {
@@ -270,7 +277,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float v[16];
             if (have_acc) {
                 tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-                tmem_ld_wait();
+                if (p.planes > 1) {
+                    float u[16];
+                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + p.NT + c0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                } else {
+                    tmem_ld_wait();
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = 0.f;
@@ -349,12 +364,31 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     return pl;
 }
 
+// pipeline stage sizing: stage = CPS chunks x (A planes + TPS taps x B planes); prefer all kw taps of a halo line in one stage and >= 3
+// stages; shrink the chunk group, then the tap group, until at least 2 stages fit in shared memory
+static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS, int &D, int &stage) {
+    const int budget = 196 * 1024;
+    const int a_plane = pl.a_rows * pl.swz, b_plane = pl.NT * pl.swz;
+    auto bytes = [&](int cps, int tps) { return cps * planes * (a_plane + tps * b_plane); };
+    TPS = pl.halo ? kw : 1;
+    CPS = pl.nchunks;
+    while (CPS > 1 && 3 * bytes(CPS, TPS) > budget) --CPS;
+    while (TPS > 1 && 2 * bytes(CPS, TPS) > budget) --TPS;
+    if (2 * bytes(CPS, TPS) > budget) return false;
+    stage = bytes(CPS, TPS);
+    D = budget / stage;
+    if (D > kTcMaxStages) D = kTcMaxStages;
+    return true;
+}
+
 bool conv_tc_wgrad_supported(const ConvGeom &g);
 size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision);
 
 bool conv_tc_supported(const ConvGeom &g, int pass) {
     if (pass == 2) return conv_tc_wgrad_supported(g);
-    return make_plan(g, pass).ok && tmap_encode_fn() != nullptr;
+    const TcPlan pl = make_plan(g, pass);
+    int a, b, c, d;
+    return pl.ok && plan_stages(pl, g.kw, 2, a, b, c, d) && tmap_encode_fn() != nullptr;
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -362,8 +396,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // number of weight replicas: as many as fit in ~16 MB, at most 16
 static int weight_reps(const TcPlan &pl, int T, int planes) {
     const size_t one = (size_t)planes * T * pl.Np * pl.Kp * 2;
-    int r = (int)((16u << 20) / (one ? one : 1));
-    return r < 1 ? 1 : r > 16 ? 16 : r;
+    (void)one;
+    return 1;   // measured on B200: replication does not change the kernel time (the weight tiles are not an L2 hot spot); kept for experiments
 }
 
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
@@ -411,15 +445,8 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     // the TMA writes only (128 + kw - 1) rows in halo mode; the transaction byte count must match what is written
     const int a_rows_loaded = pl.halo ? 128 + g.kw - 1 : 128;
     p.b_plane_bytes = pl.NT * pl.swz;
-    p.a_slot_bytes = planes * p.a_plane_bytes;
-    p.b_slot_bytes = planes * p.b_plane_bytes;
-    const int budget = 200 * 1024;
-    p.DA = pl.halo ? 3 : 4;
-    p.DB = 8;
-    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DB > 3) --p.DB;
-    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DA > 2) --p.DA;
-    while (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget && p.DB > 2) --p.DB;
-    if (p.DA * p.a_slot_bytes + p.DB * p.b_slot_bytes > budget) return MDT_EUNSUPPORTED;
+    if (!plan_stages(pl, g.kw, planes, p.CPS, p.TPS, p.D, p.stage_bytes)) return MDT_EUNSUPPORTED;
+    p.a_region_bytes = p.CPS * planes * p.a_plane_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
     p.wreps = weight_reps(pl, T, planes);
 
@@ -438,7 +465,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     }
     p.a_tx_bytes = a_rows_loaded * pl.swz;   // expect_tx must equal the bytes the TMA delivers (the box), not the padded buffer pitch
 
-    const size_t smem = (size_t)p.DA * p.a_slot_bytes + (size_t)p.DB * p.b_slot_bytes + 1024;
+    const size_t smem = (size_t)p.D * p.stage_bytes + 1024;
     static bool attr = false;
     if (!attr) { if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER; attr = true; }
     dim3 grid((unsigned)((long long)g.n * pl.RD * p.tiles_h * p.tiles_w), pl.n_tiles_n);
