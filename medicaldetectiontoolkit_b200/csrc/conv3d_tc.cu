@@ -26,12 +26,15 @@ namespace mdt {
 using namespace tc;
 
 // ------------------------------------------------------------------------------------------------ operand preparation kernels
-// fp32 [rows, C] -> bf16 planes [planes][rows, Cp] (hi, lo), channels zero-padded to Cp (multiple of 16)
+// fp32 [rows, C] -> bf16 planes (hi, lo), channels zero-padded to Cp (multiple of 16).
+//   inter_w = 0: plane-major  [plane][rows][Cp]                       (wgrad operands)
+//   inter_w > 0: line-interleaved [line][plane][inter_w voxels][Cp]   (fprop/dgrad A operand: both planes of a W-line are adjacent, so ONE
+//                TMA box {chunk, voxels, 2 planes} fetches the hi and lo halo line together); rows = lines * inter_w
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C,
-                                                        int Cp, int planes) {
+                                                        int Cp, int planes, int inter_w) {
     const int groups = Cp / 8;  // 8 channels (16 bytes of bf16) per thread
     const long long total = rows * groups;
-    const long long plane_stride = rows * Cp;
+    const long long plane_stride = inter_w > 0 ? (long long)inter_w * Cp : rows * Cp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / groups;
         const int c0 = (int)(i % groups) * 8;
@@ -44,8 +47,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
             hi[k] = __float2bfloat16_rn(v[k]);
             lo[k] = __float2bfloat16_rn(v[k] - __bfloat162float(hi[k]));
         }
-        *reinterpret_cast<uint4 *>(dst + r * Cp + c0) = *reinterpret_cast<const uint4 *>(hi);
-        if (planes > 1) *reinterpret_cast<uint4 *>(dst + plane_stride + r * Cp + c0) = *reinterpret_cast<const uint4 *>(lo);
+        long long off;
+        if (inter_w > 0) { const long long line = r / inter_w; const int w = (int)(r % inter_w); off = (line * planes * inter_w + w) * Cp + c0; }
+        else off = r * Cp + c0;
+        *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(hi);
+        if (planes > 1) *reinterpret_cast<uint4 *>(dst + off + plane_stride) = *reinterpret_cast<const uint4 *>(lo);
     }
 }
 
@@ -66,10 +72,12 @@ __global__ void __launch_bounds__(256) pack_weights_tc_kernel(const float *__res
         else           { if (n < cin && k < cout) v = w[((size_t)k * cin + n) * T + t]; }
         const __nv_bfloat16 hi = __float2bfloat16_rn(v);
         const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-        for (int r = 0; r < reps; ++r) {
-            dst[(size_t)r * planes * total + i] = hi;
-            if (planes > 1) dst[(size_t)r * planes * total + total + i] = lo;
-        }
+        // layout [T][plane][Np][Kp]: the planes of a tap are adjacent, so one TMA box {chunk, NT, planes, taps} fetches a whole stage
+        const long long per_tap = (long long)Np * Kp;
+        const long long o = ((long long)t * planes) * per_tap + (long long)n * Kp + k;
+        dst[o] = hi;
+        if (planes > 1) dst[o + per_tap] = lo;
+        (void)reps;
     }
 }
 
@@ -87,7 +95,7 @@ struct TcConvParams {
     int BW, BH, halo;     // tile = BH lines x BW voxels = 128 rows; halo mode iff BH == 1
     int tiles_w, tiles_h;
     int CPS, TPS, D;      // K chunks per stage, taps per stage (KW in halo mode, 1 otherwise), ring depth
-    int a_plane_bytes, b_plane_bytes, a_tx_bytes, stage_bytes, a_region_bytes;
+    int a_plane_bytes, b_plane_bytes, a_tx_bytes, stage_bytes, a_region_bytes, a_chunk_bytes, b_chunk_bytes;
     int relu;
     int wreps;            // weight replicas in global memory
     const float *bias, *residual;
@@ -141,7 +149,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nb = t / p.RD;
     const int rw0 = tw * p.BW, rh0 = th * p.BH;
     const int n0 = blockIdx.y * p.NT;
-    const int T = p.KD * p.KH * p.KW;
     const int chunk_elems = p.swz >> 1;
     const int ngroups = (p.nchunks + p.CPS - 1) / p.CPS;
 
@@ -171,8 +178,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 1;   // parity to wait for on `empty` (fresh barrier: the "previous" phase counts as complete)
-            const int rep = blockIdx.x % p.wreps;
-            for (int kd = 0; kd < p.KD; ++kd)
+                    for (int kd = 0; kd < p.KD; ++kd)
                 for (int kh = 0; kh < p.KH; ++kh) {
                     int d_src, h_src;
                     if (!tc_step_coords(p, rd, rh0, kd, kh, d_src, h_src)) continue;
@@ -185,17 +191,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             int w_start;
                             if (p.halo) w_start = p.dgrad ? rw0 + p.pw - (p.KW - 1) : rw0 - p.pw;
                             else        w_start = p.dgrad ? rw0 + p.pw - kw0 : rw0 - p.pw + kw0;
-                            for (int c = 0; c < cn; ++c)
-                                for (int pl = 0; pl < p.planes; ++pl)
-                                    tma_load_5d(st + (size_t)(c * p.planes + pl) * p.a_plane_bytes, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start,
-                                                h_src, d_src, nb + pl * p.NB);
-                            uint8_t *sb = st + p.a_region_bytes;
-                            for (int k = 0; k < p.TPS; ++k) {
-                                const int tap = (kd * p.KH + kh) * p.KW + kw0 + k;
-                                for (int c = 0; c < cn; ++c)
+                            const int tap0 = (kd * p.KH + kh) * p.KW + kw0;
+                            for (int c = 0; c < cn; ++c) {
+                                uint8_t *ab = st + (size_t)c * p.a_chunk_bytes;
+                                if (p.halo) {   // one box = both planes of the halo line: {chunk, voxels, planes, 1, 1}
+                                    tma_load_5d(ab, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start, 0, h_src, nb * p.SD + d_src);
+                                } else {
                                     for (int pl = 0; pl < p.planes; ++pl)
-                                        tma_load_3d(sb + (size_t)((k * p.CPS + c) * p.planes + pl) * p.b_plane_bytes, &tmB, &full[s],
-                                                    (c_lo + c) * chunk_elems, n0, tap + (rep * p.planes + pl) * T);
+                                        tma_load_5d(ab + (size_t)pl * p.a_plane_bytes, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start, pl, h_src,
+                                                    nb * p.SD + d_src);
+                                }
+                                // one box = all taps of the stage x both planes: {chunk, NT, planes, TPS}
+                                tma_load_4d(st + p.a_region_bytes + (size_t)c * p.b_chunk_bytes, &tmB, &full[s], (c_lo + c) * chunk_elems, n0, 0, tap0);
                             }
                             if (++s == p.D) { s = 0; ph ^= 1; }
                         }
@@ -224,11 +231,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             mbar_wait(&full[s], ph);
                             tc_fence_after();
                             const uint32_t st = smem_base + s * p.stage_bytes;
-                            for (int k = 0; k < p.TPS; ++k) {
+                            const int ktaps = min(p.TPS, p.KW - kw0);   // the last tap group of a line may be short
+                            for (int k = 0; k < ktaps; ++k) {
                                 const int shift = p.halo ? (p.dgrad ? p.KW - 1 - (kw0 + k) : kw0 + k) : 0;
                                 for (int c = 0; c < cn; ++c) {
-                                    const uint32_t a_hi = st + (c * p.planes) * p.a_plane_bytes + shift * p.swz;
-                                    const uint32_t b_hi = st + p.a_region_bytes + ((k * p.CPS + c) * p.planes) * p.b_plane_bytes;
+                                    const uint32_t a_hi = st + c * p.a_chunk_bytes + shift * p.swz;
+                                    const uint32_t b_hi = st + p.a_region_bytes + c * p.b_chunk_bytes + (k * p.planes) * p.b_plane_bytes;
                                     uint64_t da = dtmpl | (uint64_t)((a_hi >> 4) & 0x3FFF);
                                     uint64_t db = dtmpl | (uint64_t)((b_hi >> 4) & 0x3FFF);
                                     uint64_t dal = dtmpl | (uint64_t)(((a_hi + p.a_plane_bytes) >> 4) & 0x3FFF);
@@ -324,6 +332,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
 struct TcPlan {
     bool ok = false;
     int Kc, Kp, Nc, Np, NT, n_tiles_n, swz, nchunks, BW, BH, halo, a_rows;
@@ -340,12 +350,13 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     pl.Nc = dgrad ? g.cin : g.cout;
     pl.RD = dgrad ? g.d : g.od; pl.RH = dgrad ? g.h : g.oh; pl.RW = dgrad ? g.w : g.ow;
     pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
-    pl.Kp = ceil_div(pl.Kc, 16) * 16;
+    // K padding: one swizzle-span chunk for <= 64 channels (few, large TMA boxes), 64-channel chunks above
+    pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;
     pl.Np = ceil_div(pl.Nc, 16) * 16;
     pl.NT = pl.Np <= 128 ? pl.Np : 128;
     pl.n_tiles_n = ceil_div(pl.Np, pl.NT);
     if (pl.Np % pl.NT) pl.Np = pl.n_tiles_n * pl.NT;   // keep the TMA box inside the packed weight tensor
-    pl.swz = (pl.Kp % 64 == 0) ? 128 : (pl.Kp % 32 == 0) ? 64 : 32;
+    pl.swz = pl.Kp >= 64 ? 128 : pl.Kp * 2;
     pl.nchunks = pl.Kp / (pl.swz / 2);
     if (pl.RW >= 128) { pl.BW = 128; pl.BH = 1; }
     else {
@@ -356,7 +367,7 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
         if (g.sh != 1) return pl;        // generic mode loads BH consecutive source lines
     }
     pl.halo = pl.BH == 1;
-    pl.a_rows = pl.halo ? ceil_div(128 + g.kw - 1, 8) * 8 : 128;
+    pl.a_rows = pl.halo ? 128 + g.kw - 1 : 128;
     if (128 + g.kw - 1 > 256) return pl;
     pl.src_rows = (long long)g.n * pl.SD * pl.SH * pl.SW;
     pl.dst_rows = (long long)g.n * pl.RD * pl.RH * pl.RW;
@@ -366,10 +377,13 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
 
 // pipeline stage sizing: stage = CPS chunks x (A planes + TPS taps x B planes); prefer all kw taps of a halo line in one stage and >= 3
 // stages; shrink the chunk group, then the tap group, until at least 2 stages fit in shared memory
+static int a_rows_loaded(const TcPlan &pl, int kw) { return pl.halo ? 128 + kw - 1 : 128; }
+static int a_chunk_bytes_of(const TcPlan &pl, int kw, int planes) { return (int)align_up((size_t)planes * a_rows_loaded(pl, kw) * pl.swz, 1024); }
+
 static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS, int &D, int &stage) {
     const int budget = 196 * 1024;
-    const int a_plane = pl.a_rows * pl.swz, b_plane = pl.NT * pl.swz;
-    auto bytes = [&](int cps, int tps) { return cps * planes * (a_plane + tps * b_plane); };
+    const int a_chunk = a_chunk_bytes_of(pl, kw, planes), b_plane = pl.NT * pl.swz;
+    auto bytes = [&](int cps, int tps) { return cps * (a_chunk + (int)align_up((size_t)tps * planes * b_plane, 1024)); };
     TPS = pl.halo ? kw : 1;
     CPS = pl.nchunks;
     while (CPS > 1 && 3 * bytes(CPS, TPS) > budget) --CPS;
@@ -377,7 +391,7 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     if (2 * bytes(CPS, TPS) > budget) return false;
     stage = bytes(CPS, TPS);
     D = budget / stage;
-    if (D > kTcMaxStages) D = kTcMaxStages;
+    if (D > 3) D = 3;   // 3 stages cover the TMA latency; a small footprint lets several CTAs share an SM and overlap their prologues/epilogues
     return true;
 }
 
@@ -391,7 +405,6 @@ bool conv_tc_supported(const ConvGeom &g, int pass) {
     return pl.ok && plan_stages(pl, g.kw, 2, a, b, c, d) && tmap_encode_fn() != nullptr;
 }
 
-static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // number of weight replicas: as many as fit in ~16 MB, at most 16
 static int weight_reps(const TcPlan &pl, int T, int planes) {
@@ -425,7 +438,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
         const long long total = pl.src_rows * (pl.Kp / 8);
         long long blocks = ceil_div<long long>(total, 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes);
+        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes, pl.SW);
         int rc = launch_status();
         if (rc) return rc;
         const long long wt = (long long)T * pl.Np * pl.Kp;
@@ -441,29 +454,31 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     p.Cn = pl.Nc; p.Np = pl.Np; p.NT = pl.NT; p.nchunks = pl.nchunks; p.swz = pl.swz; p.planes = planes;
     p.BW = pl.BW; p.BH = pl.BH; p.halo = pl.halo;
     p.tiles_w = ceil_div(pl.RW, pl.BW); p.tiles_h = ceil_div(pl.RH, pl.BH);
-    p.a_plane_bytes = pl.a_rows * pl.swz;
-    // the TMA writes only (128 + kw - 1) rows in halo mode; the transaction byte count must match what is written
-    const int a_rows_loaded = pl.halo ? 128 + g.kw - 1 : 128;
+    const int rows_loaded = a_rows_loaded(pl, g.kw);
+    p.a_plane_bytes = rows_loaded * pl.swz;                       // plane 1 follows plane 0 directly (one TMA box delivers both)
+    p.a_chunk_bytes = a_chunk_bytes_of(pl, g.kw, planes);
     p.b_plane_bytes = pl.NT * pl.swz;
     if (!plan_stages(pl, g.kw, planes, p.CPS, p.TPS, p.D, p.stage_bytes)) return MDT_EUNSUPPORTED;
-    p.a_region_bytes = p.CPS * planes * p.a_plane_bytes;
+    p.b_chunk_bytes = (int)align_up((size_t)p.TPS * planes * p.b_plane_bytes, 1024);
+    p.a_region_bytes = p.CPS * p.a_chunk_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
     p.wreps = weight_reps(pl, T, planes);
 
-    // tensor maps.  A: bf16 [planes*N][SD][SH][SW][Kp];  B: bf16 [planes*T][Np][Kp]
+    // tensor maps.  A: bf16 [N*SD][SH][plane][SW][Kp] (N and D merged: out-of-range d taps are skipped explicitly, never fetched);
+    //               B: bf16 [T][plane][Np][Kp]
     CUtensorMap tmA, tmB;
     {
-        const uint64_t dims[5] = {(uint64_t)pl.Kp, (uint64_t)pl.SW, (uint64_t)pl.SH, (uint64_t)pl.SD, (uint64_t)g.n * planes};
-        const uint64_t strides[4] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.SW * pl.Kp * 2, (uint64_t)pl.SH * pl.SW * pl.Kp * 2,
-                                     (uint64_t)pl.SD * pl.SH * pl.SW * pl.Kp * 2};
-        const uint32_t box[5] = {(uint32_t)(pl.swz / 2), (uint32_t)(pl.halo ? a_rows_loaded : pl.BW), (uint32_t)pl.BH, 1u, 1u};
+        const uint64_t line = (uint64_t)pl.SW * pl.Kp * 2;
+        const uint64_t dims[5] = {(uint64_t)pl.Kp, (uint64_t)pl.SW, (uint64_t)planes, (uint64_t)pl.SH, (uint64_t)g.n * pl.SD};
+        const uint64_t strides[4] = {(uint64_t)pl.Kp * 2, line, line * planes, line * planes * pl.SH};
+        const uint32_t box[5] = {(uint32_t)(pl.swz / 2), (uint32_t)(pl.halo ? rows_loaded : pl.BW), (uint32_t)(pl.halo ? planes : 1), (uint32_t)pl.BH, 1u};
         if (!encode_bf16_tmap(&tmA, xs, 5, dims, strides, box, pl.swz)) return MDT_EDRIVER;
-        const uint64_t bdims[3] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)T * planes * p.wreps};
-        const uint64_t bstr[2] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.Np * pl.Kp * 2};
-        const uint32_t bbox[3] = {(uint32_t)(pl.swz / 2), (uint32_t)pl.NT, 1u};
-        if (!encode_bf16_tmap(&tmB, wp, 3, bdims, bstr, bbox, pl.swz)) return MDT_EDRIVER;
+        const uint64_t bdims[4] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)planes, (uint64_t)T};
+        const uint64_t bstr[3] = {(uint64_t)pl.Kp * 2, (uint64_t)pl.Np * pl.Kp * 2, (uint64_t)planes * pl.Np * pl.Kp * 2};
+        const uint32_t bbox[4] = {(uint32_t)(pl.swz / 2), (uint32_t)pl.NT, (uint32_t)planes, (uint32_t)p.TPS};
+        if (!encode_bf16_tmap(&tmB, wp, 4, bdims, bstr, bbox, pl.swz)) return MDT_EDRIVER;
     }
-    p.a_tx_bytes = a_rows_loaded * pl.swz;   // expect_tx must equal the bytes the TMA delivers (the box), not the padded buffer pitch
+    p.a_tx_bytes = rows_loaded * pl.swz;   // per plane; expect_tx must equal the bytes the TMA boxes deliver
 
     const size_t smem = (size_t)p.D * p.stage_bytes + 1024;
     static bool attr = false;

@@ -19,7 +19,7 @@
 namespace mdt {
 using namespace tc;
 
-__global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes);
+__global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes, int inter_w);
 
 struct TcWgradParams {
     int NB, OD, OH, OW, D, H, W;
@@ -306,7 +306,7 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp) {
         long long blocks = ceil_div<long long>(rows * (Cp / 8), 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, C, Cp, planes);
+        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, C, Cp, planes, 0);
         return launch_status();
     };
     int rc = split(dy, ys, rows_y, g.cout, w.co_p);
