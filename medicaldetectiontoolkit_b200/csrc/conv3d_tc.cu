@@ -21,6 +21,7 @@
 // (TMEM -> registers -> bias / residual / ReLU -> global fp32 NDHWC).
 #include "conv3d_common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace mdt {
 using namespace tc;
@@ -97,6 +98,7 @@ struct TcConvParams {
     int CPS, TPS, D;      // K chunks per stage, taps per stage (KW in halo mode, 1 otherwise), ring depth
     int a_plane_bytes, b_plane_bytes, a_tx_bytes, stage_bytes, a_region_bytes, a_chunk_bytes, b_chunk_bytes;
     int relu;
+    int Q;                // independent accumulator chains per MMA type
     int wreps;            // weight replicas in global memory
     const float *bias, *residual;
     float *out;
@@ -138,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ uint64_t full[kTcMaxStages], empty[kTcMaxStages], accum_full;
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_have_acc;
+    __shared__ uint32_t s_n1, s_n2;   // accumulators actually written, per MMA type
     __shared__ float s_bias[128];
 
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -164,9 +167,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int c = threadIdx.x - 64;
         s_bias[c] = (p.bias && n0 + c < p.Cn) ? __ldg(p.bias + n0 + c) : 0.f;
     }
-    const int acc_cols = p.planes > 1 ? 2 * p.NT : p.NT;
+    // Q independent accumulator chains per MMA type (see the MMA issuer): type-1 accumulators are acc1_cols wide, type-2 (split-bf16 only) NT wide
+    const int acc1_cols = p.planes > 1 ? 2 * p.NT : p.NT;
+    const int Q = p.Q;
+    const int acc2_base = Q * acc1_cols;
+    const int acc_total = acc2_base + (p.planes > 1 ? Q * p.NT : 0);
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < acc_cols) tmem_cols <<= 1;
+    while ((int)tmem_cols < acc_total) tmem_cols <<= 1;
     if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -218,9 +225,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t dtmpl = make_smem_desc(0, 16, 8u * p.swz, layout_type_for_swizzle_bytes(p.swz));
             const int ksteps = p.swz / 32;
             const uint32_t smem_base = smem_u32(smem);
+            // A chain of tcgen05.mma into ONE accumulator is latency-bound for the small N of these layers (each MMA must see the previous
+            // result; measured: a CTA ran ~5x below the tensor-pipe rate and only co-resident CTAs overlapped).  So successive MMAs rotate over
+            // Q independent accumulators per type (type 1: A_hi x [B_hi;B_lo], 2*NT columns; type 2: A_lo x B_hi, NT columns) and the epilogue
+            // adds them up.
             int s = 0;
             uint32_t ph = 0;
-            uint32_t acc = 0;
+            uint32_t n1 = 0, n2 = 0;          // MMAs issued per type
+            uint32_t q1 = 0, q2 = 0;          // round-robin cursors
             for (int kd = 0; kd < p.KD; ++kd)
                 for (int kh = 0; kh < p.KH; ++kh) {
                     int d_src, h_src;
@@ -240,19 +252,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     uint64_t da = dtmpl | (uint64_t)((a_hi >> 4) & 0x3FFF);
                                     uint64_t db = dtmpl | (uint64_t)((b_hi >> 4) & 0x3FFF);
                                     uint64_t dal = dtmpl | (uint64_t)(((a_hi + p.a_plane_bytes) >> 4) & 0x3FFF);
-                                    if (p.planes > 1) {
-                                        for (int j = 0; j < ksteps; ++j) {
-                                            umma_bf16(tmem, da, db, idesc2, acc);        // A_hi x [B_hi ; B_lo]
-                                            umma_bf16(tmem, dal, db, idesc1, 1);         // A_lo x B_hi
-                                            acc = 1;
-                                            da += 2; db += 2; dal += 2;                  // +32 bytes along K
+                                    for (int j = 0; j < ksteps; ++j) {
+                                        umma_bf16(tmem + q1 * acc1_cols, da, db, p.planes > 1 ? idesc2 : idesc1, n1 >= (uint32_t)Q);
+                                        ++n1;
+                                        if (++q1 == (uint32_t)Q) q1 = 0;
+                                        if (p.planes > 1) {
+                                            umma_bf16(tmem + acc2_base + q2 * p.NT, dal, db, idesc1, n2 >= (uint32_t)Q);
+                                            ++n2;
+                                            if (++q2 == (uint32_t)Q) q2 = 0;
                                         }
-                                    } else {
-                                        for (int j = 0; j < ksteps; ++j) {
-                                            umma_bf16(tmem, da, db, idesc1, acc);
-                                            acc = 1;
-                                            da += 2; db += 2;
-                                        }
+                                        da += 2; db += 2; dal += 2;          // +32 bytes along K
                                     }
                                 }
                             }
@@ -261,6 +270,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                 }
+            const uint32_t acc = n1;
+            *(volatile uint32_t *)&s_n1 = n1 < (uint32_t)Q ? n1 : (uint32_t)Q;
+            *(volatile uint32_t *)&s_n2 = n2 < (uint32_t)Q ? n2 : (uint32_t)Q;
+            __threadfence_block();
             if (acc) {
                 umma_commit(&accum_full);
             } else {   // no tap contributed (e.g. a dgrad row of a strided conv that no output touches): the result is bias / zero only
@@ -274,6 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&accum_full, 0);
         tc_fence_after();
         const bool have_acc = (*(volatile uint32_t *)&s_have_acc) != 0u;
+        const uint32_t n1_used = *(volatile uint32_t *)&s_n1, n2_used = *(volatile uint32_t *)&s_n2;
         const int q = warp & 3;              // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;
         const int hi_ = r / p.BW, wi = r % p.BW;
@@ -283,20 +297,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool vec4 = (p.Cn % 4 == 0);
         for (int c0 = 0; c0 < p.NT; c0 += 16) {
             float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0.f;
             if (have_acc) {
-                tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-                if (p.planes > 1) {
-                    float u[16];
-                    tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + p.NT + c0, u);
+                const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+                float u[16];
+                for (uint32_t a = 0; a < n1_used; ++a) {
+                    tmem_ld16(lane_base + a * acc1_cols + c0, u);
                     tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += u[j];
-                } else {
-                    tmem_ld_wait();
-                }
-            } else {
+                    if (p.planes > 1) {
+                        tmem_ld16(lane_base + a * acc1_cols + p.NT + c0, u);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                        for (int j = 0; j < 16; ++j) v[j] += u[j];
+                    }
+                }
+                for (uint32_t a = 0; a < n2_used; ++a) {
+                    tmem_ld16(lane_base + acc2_base + a * p.NT + c0, u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += u[j];
+                }
             }
             if (!valid) continue;
 #pragma unroll
@@ -389,9 +412,12 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     while (CPS > 1 && 3 * bytes(CPS, TPS) > budget) --CPS;
     while (TPS > 1 && 2 * bytes(CPS, TPS) > budget) --TPS;
     if (2 * bytes(CPS, TPS) > budget) return false;
+    // experiment knobs (tools/conv_layer_bench.py): MDT_TC_TPS caps the taps per stage, MDT_TC_D sets the ring depth
+    if (const char *e = getenv("MDT_TC_TPS")) { const int v = atoi(e); if (v >= 1 && v < TPS) TPS = v; }
     stage = bytes(CPS, TPS);
     D = budget / stage;
     if (D > 3) D = 3;   // 3 stages cover the TMA latency; a small footprint lets several CTAs share an SM and overlap their prologues/epilogues
+    if (const char *e = getenv("MDT_TC_D")) { const int v = atoi(e); if (v >= 1 && v <= kTcMaxStages && v * stage <= budget) D = v; }
     return true;
 }
 
@@ -462,6 +488,10 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     p.b_chunk_bytes = (int)align_up((size_t)p.TPS * planes * p.b_plane_bytes, 1024);
     p.a_region_bytes = p.CPS * p.a_chunk_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
+    p.Q = 512 / ((planes > 1 ? 3 : 1) * pl.NT);
+    if (p.Q > 4) p.Q = 4;
+    if (p.Q < 1) p.Q = 1;
+    if (const char *e = getenv("MDT_TC_Q")) { const int v = atoi(e); if (v >= 1 && v <= p.Q) p.Q = v; }
     p.wreps = weight_reps(pl, T, planes);
 
     // tensor maps.  A: bf16 [N*SD][SH][plane][SW][Kp] (N and D merged: out-of-range d taps are skipped explicitly, never fetched);

@@ -133,27 +133,29 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 tc_fence_after();
                 const uint32_t y_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
                 const uint32_t x0 = y_hi + p.planes * p.y_plane_bytes;
+                // which column blocks take part for this line
+                uint32_t live = 0;
                 for (int b = 0; b < ncb; ++b) {
                     int kd, kh, xc;
                     wg_decode_cb(p, cb0 + b, kd, kh, xc);
                     const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
-                    if (d < 0 || d >= p.D || h < 0 || h >= p.H) continue;
-                    const uint32_t xb = x0 + b * p.x_buf_bytes;
-                    const uint32_t dcol = tmem + b * ncols;
-                    uint32_t acc = (started >> b) & 1u;
-                    for (int k = 0; k < p.ksteps; ++k) {
-                        const uint32_t ya = y_hi + k * 16 * p.swy, xa = xb + k * 16 * p.swx;
-                        const uint64_t dy_hi = make_smem_desc(ya, p.y_chunk_bytes, 8 * p.swy, lty);
-                        const uint64_t dx_hi = make_smem_desc(xa, p.swx, 8 * p.swx, ltx);      // LBO = one row: next N chunk = next kw shift
-                        umma_bf16(dcol, dy_hi, dx_hi, idesc, acc);
-                        acc = 1;
-                        if (p.planes > 1) {
-                            const uint64_t dx_lo = make_smem_desc(xa + p.x_plane_bytes, p.swx, 8 * p.swx, ltx);
-                            umma_bf16(dcol, dy_hi, dx_lo, idesc, 1);
-                            if (!p.mtrick) umma_bf16(dcol, make_smem_desc(ya + p.y_plane_bytes, p.y_chunk_bytes, 8 * p.swy, lty), dx_hi, idesc, 1);
+                    if (d >= 0 && d < p.D && h >= 0 && h < p.H) live |= 1u << b;
+                }
+                // K steps outermost, column blocks innermost: consecutive MMAs write DIFFERENT accumulators, so the tensor pipe never waits on
+                // the accumulate dependency of a single chain
+                for (int k = 0; k < p.ksteps; ++k) {
+                    const uint32_t ya = y_hi + k * 16 * p.swy;
+                    const uint64_t dy_hi = make_smem_desc(ya, p.y_chunk_bytes, 8 * p.swy, lty);
+                    const int npass = p.planes > 1 ? (p.mtrick ? 2 : 3) : 1;
+                    for (int pass = 0; pass < npass; ++pass) {       // pass 0: dy_hi*x_hi, 1: dy_hi*x_lo, 2: dy_lo*x_hi — one sweep over the blocks each
+                        const uint64_t dya = pass == 2 ? make_smem_desc(ya + p.y_plane_bytes, p.y_chunk_bytes, 8 * p.swy, lty) : dy_hi;
+                        for (int b = 0; b < ncb; ++b) {
+                            if (!((live >> b) & 1u)) continue;
+                            const uint32_t xa = x0 + b * p.x_buf_bytes + k * 16 * p.swx + (pass == 1 ? p.x_plane_bytes : 0);
+                            umma_bf16(tmem + b * ncols, dya, make_smem_desc(xa, p.swx, 8 * p.swx, ltx), idesc, (started >> b) & 1u);   // LBO = one row
+                            started |= 1u << b;
                         }
                     }
-                    started |= 1u << b;
                 }
                 umma_commit(&empty[s]);
             }
