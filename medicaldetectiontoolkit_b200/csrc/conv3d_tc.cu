@@ -415,8 +415,10 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     // experiment knobs (tools/conv_layer_bench.py): MDT_TC_TPS caps the taps per stage, MDT_TC_D sets the ring depth
     if (const char *e = getenv("MDT_TC_TPS")) { const int v = atoi(e); if (v >= 1 && v < TPS) TPS = v; }
     stage = bytes(CPS, TPS);
-    D = budget / stage;
-    if (D > 3) D = 3;   // 3 stages cover the TMA latency; a small footprint lets several CTAs share an SM and overlap their prologues/epilogues
+    // Measured on B200 (profiles/r01_mma_rate.txt, r01_stage_sweep.txt): one thread cannot issue tcgen05.mma faster than ~60 cycles each, so for
+    // the small N of these layers a single CTA leaves the tensor pipe idle; co-resident CTAs fill it.  Residency beats ring depth: keep the
+    // footprint minimal (1 stage when a stage is large, 2 when small) so that 2-4 CTAs share an SM and overlap each other's loads/epilogues.
+    D = stage > 40 * 1024 ? 1 : 2;
     if (const char *e = getenv("MDT_TC_D")) { const int v = atoi(e); if (v >= 1 && v <= kTcMaxStages && v * stage <= budget) D = v; }
     return true;
 }
@@ -488,9 +490,7 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     p.b_chunk_bytes = (int)align_up((size_t)p.TPS * planes * p.b_plane_bytes, 1024);
     p.a_region_bytes = p.CPS * p.a_chunk_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
-    p.Q = 512 / ((planes > 1 ? 3 : 1) * pl.NT);
-    if (p.Q > 4) p.Q = 4;
-    if (p.Q < 1) p.Q = 1;
+    p.Q = 1;   // accumulator chains: measured to make no difference (the accumulate dependency is not the limiter); 1 keeps TMEM small
     if (const char *e = getenv("MDT_TC_Q")) { const int v = atoi(e); if (v >= 1 && v <= p.Q) p.Q = v; }
     p.wreps = weight_reps(pl, T, planes);
 

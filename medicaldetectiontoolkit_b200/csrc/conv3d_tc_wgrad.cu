@@ -123,6 +123,9 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         if (lane == 0) {
             const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
             const uint32_t lty = layout_type_for_swizzle_bytes(p.swy), ltx = layout_type_for_swizzle_bytes(p.swx);
+            // descriptor templates (everything but the 14-bit start address); the x descriptor's LBO is ONE ROW: next N chunk = next kw shift
+            const uint64_t ytmpl = make_smem_desc(0, p.y_chunk_bytes, 8 * p.swy, lty), xtmpl = make_smem_desc(0, p.swx, 8 * p.swx, ltx);
+            const uint64_t ystep = (uint64_t)((16 * p.swy) >> 4), xstep = (uint64_t)((16 * p.swx) >> 4);
             uint32_t started = 0;
             int it = 0;
             for (long long u = split; u < p.units; u += p.splits, ++it) {
@@ -133,29 +136,29 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 tc_fence_after();
                 const uint32_t y_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
                 const uint32_t x0 = y_hi + p.planes * p.y_plane_bytes;
-                // which column blocks take part for this line
-                uint32_t live = 0;
+                // (measured: interleaving the column blocks inside the K loop does not help — the accumulate dependency is not the limiter, the
+                //  single-thread issue rate is — so keep the order with the fewest instructions per MMA: descriptors advance by integer adds)
                 for (int b = 0; b < ncb; ++b) {
                     int kd, kh, xc;
                     wg_decode_cb(p, cb0 + b, kd, kh, xc);
                     const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
-                    if (d >= 0 && d < p.D && h >= 0 && h < p.H) live |= 1u << b;
-                }
-                // K steps outermost, column blocks innermost: consecutive MMAs write DIFFERENT accumulators, so the tensor pipe never waits on
-                // the accumulate dependency of a single chain
-                for (int k = 0; k < p.ksteps; ++k) {
-                    const uint32_t ya = y_hi + k * 16 * p.swy;
-                    const uint64_t dy_hi = make_smem_desc(ya, p.y_chunk_bytes, 8 * p.swy, lty);
-                    const int npass = p.planes > 1 ? (p.mtrick ? 2 : 3) : 1;
-                    for (int pass = 0; pass < npass; ++pass) {       // pass 0: dy_hi*x_hi, 1: dy_hi*x_lo, 2: dy_lo*x_hi — one sweep over the blocks each
-                        const uint64_t dya = pass == 2 ? make_smem_desc(ya + p.y_plane_bytes, p.y_chunk_bytes, 8 * p.swy, lty) : dy_hi;
-                        for (int b = 0; b < ncb; ++b) {
-                            if (!((live >> b) & 1u)) continue;
-                            const uint32_t xa = x0 + b * p.x_buf_bytes + k * 16 * p.swx + (pass == 1 ? p.x_plane_bytes : 0);
-                            umma_bf16(tmem + b * ncols, dya, make_smem_desc(xa, p.swx, 8 * p.swx, ltx), idesc, (started >> b) & 1u);   // LBO = one row
-                            started |= 1u << b;
+                    if (d < 0 || d >= p.D || h < 0 || h >= p.H) continue;
+                    const uint32_t dcol = tmem + b * ncols;
+                    uint64_t dyh = ytmpl | (uint64_t)((y_hi >> 4) & 0x3FFF);
+                    uint64_t dyl = ytmpl | (uint64_t)(((y_hi + p.y_plane_bytes) >> 4) & 0x3FFF);
+                    uint64_t dxh = xtmpl | (uint64_t)(((x0 + b * p.x_buf_bytes) >> 4) & 0x3FFF);
+                    uint64_t dxl = xtmpl | (uint64_t)(((x0 + b * p.x_buf_bytes + p.x_plane_bytes) >> 4) & 0x3FFF);
+                    uint32_t acc = (started >> b) & 1u;
+                    for (int k = 0; k < p.ksteps; ++k) {
+                        umma_bf16(dcol, dyh, dxh, idesc, acc);
+                        if (p.planes > 1) {
+                            umma_bf16(dcol, dyh, dxl, idesc, 1);
+                            if (!p.mtrick) umma_bf16(dcol, dyl, dxh, idesc, 1);
                         }
+                        acc = 1;
+                        dyh += ystep; dyl += ystep; dxh += xstep; dxl += xstep;     // 16 voxel rows further along K
                     }
+                    started |= 1u << b;
                 }
                 umma_commit(&empty[s]);
             }
