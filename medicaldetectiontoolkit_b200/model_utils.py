@@ -211,8 +211,11 @@ def clip_boxes_3D(boxes, window):
 
 
 def clip_to_window(window, boxes):
-    """(model_utils.py:623-637) — note the argument order (window first)"""
-    return clip_boxes_3D(boxes, window) if boxes.shape[1] > 5 else clip_boxes_2D(boxes, window)
+    """(model_utils.py:623-637) — note the argument order (window first).  Like the reference, only the coordinate columns are clamped;
+    trailing columns (e.g. the batch index of mrcnn's sample_proposals) pass through."""
+    n = 6 if boxes.shape[1] > 5 else 4
+    clipped = clip_boxes_3D(boxes[:, :6], window) if n == 6 else clip_boxes_2D(boxes[:, :4], window)
+    return clipped if boxes.shape[1] == n else torch.cat((clipped, boxes[:, n:]), dim=1)
 
 
 def box_refinement(box, gt_box):

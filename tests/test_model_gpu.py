@@ -25,6 +25,14 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def _rel_l2(a, b):
+    """relative L2 error — the norm used for GRADIENTS that passed through ReLUs: a rounding-level change of a pre-activation near zero flips its
+    mask and changes that single gradient element by O(1) (seen on B200: max-norm 1e-1 on one element of one block while every kernel is exact to
+    6e-6 on the same tensors, tools/debug_fpn_backward.py), which the max norm reports as a gross error and the L2 norm correctly as noise."""
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
 def _fpn_run(golden_dir, tag, op1, algo):
     g = np.load(os.path.join(golden_dir, "backbone3d_%s.npz" % tag))
     cf = make_cf('retina_unet' if op1 else 'mrcnn', 3, (32, 32, 16))
@@ -47,11 +55,11 @@ def _fpn_run(golden_dir, tag, op1, algo):
         loss = sum((o * o).mean() for o in outs)
         errs["loss"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
         loss.backward()
-        errs["x_grad"] = _rel(detweights.subsample(x.grad.cpu().numpy()), g["x_grad"])
+        errs["x_grad"] = _rel_l2(detweights.subsample(x.grad.cpu().numpy()), g["x_grad"])
         params = dict(fpn.named_parameters())
         for k in g.files:
             if k.startswith("grad__"):
-                errs[k] = _rel(detweights.subsample(params[k[6:]].grad.cpu().numpy()), g[k])
+                errs[k] = _rel_l2(detweights.subsample(params[k[6:]].grad.cpu().numpy()), g[k])
         nograd = sorted(k for k, p in params.items() if p.grad is None)
         assert nograd == sorted(g["nograd"])                                       # P1_conv2.* never used (backbone.py:175)
         return errs
@@ -62,15 +70,15 @@ def _fpn_run(golden_dir, tag, op1, algo):
 @pytest.mark.parametrize("tag,op1", [("unet", True), ("mrcnn", False)])
 def test_fpn_vs_reference_fixture(golden_dir, tag, op1):
     """FPN forward + all gradients vs the fixture produced by the reference's models/backbone.py on CPU fp32, for the exact fp32 SIMT kernels
-    and for the default (tcgen05 split-bf16) path.  Forward: 1e-4 (north_star).  Gradients after a ~60-conv backward chain: 1e-3 for the fp32
-    kernels; the split-bf16 path carries ~1e-5 per conv and is held to 2e-2 end to end (per-conv bars are in tests/test_conv_gpu.py)."""
+    and for the default (tcgen05 split-bf16) path.  Forward: 1e-4 of max|ref| (north_star).  Gradients after the ~60-conv backward chain: relative L2 (see _rel_l2) 1e-3 for the fp32 kernels,
+    5e-3 for the split-bf16 path (per-conv 1e-4 bars are in tests/test_conv_gpu.py)."""
     simt = _fpn_run(golden_dir, tag, op1, 1)
     auto = _fpn_run(golden_dir, tag, op1, 0)
     print("fpn parity", tag, "simt", {k: "%.1e" % v for k, v in simt.items()}, "auto", {k: "%.1e" % v for k, v in auto.items()})
     for k, v in simt.items():
         assert v < (1e-4 if k.startswith("out") or k == "loss" else 1e-3), ("simt", k, v)
     for k, v in auto.items():
-        assert v < (1e-4 if k.startswith("out") or k == "loss" else 2e-2), ("auto", k, v)
+        assert v < (1e-4 if k.startswith("out") or k == "loss" else 5e-3), ("auto", k, v)
 
 
 def test_retina_unet_train_step_small():
