@@ -125,6 +125,12 @@ int mdt_conv3d_wgrad(const mdt_conv3d_desc *desc_host, const float *x, const flo
                      size_t workspace_bytes, void *stream);
 /* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
+/* ------------------------------------------------------------- decoder up-sampling -----------------------------------------------------------
+ * replaces: F.interpolate(x, scale_factor=(2,2,1), mode='trilinear', align_corners=False) of models/backbone.py:209-218 (P2/P1_upsample), NDHWC.
+ * x [n, d, h, w, c] -> y [n, 2d, 2h, w, c]; c % 4 == 0; backward is the exact adjoint, written as a gather (no atomics, no zero fill). */
+int mdt_upsample221_forward(const float *x, float *y, int n, int d, int h, int w, int c, void *stream);
+int mdt_upsample221_backward(const float *gy, float *gx, int n, int d, int h, int w, int c, void *stream);
+
 /* number of kernel launches issued by this library since load (all entry points) — feeds bench.py's gpu_launches */
 unsigned long long mdt_launch_count(void);
 

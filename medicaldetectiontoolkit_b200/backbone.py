@@ -55,6 +55,33 @@ class ResBlock(nn.Module):
         return self.relu(self.conv3(out) + shortcut)
 
 
+class _Upsample221(torch.autograd.Function):
+    """(2,2,1) trilinear up-sampling of a channels-last map on libmdt_b200 (csrc/resample.cu); backward = gather adjoint"""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import _lib as L
+        lib = L.load()
+        x = x.contiguous(memory_format=_CL3)
+        n, c, d, h, w = x.shape
+        y = torch.empty((n, c, 2 * d, 2 * h, w), dtype=x.dtype, device=x.device, memory_format=_CL3)
+        with torch.cuda.device(x.device):
+            L.check(lib.mdt_upsample221_forward(L.ptr(x), L.ptr(y), n, d, h, w, c, L.stream_ptr()))
+        ctx.shape = (n, c, d, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import _lib as L
+        lib = L.load()
+        n, c, d, h, w = ctx.shape
+        gy = gy.contiguous(memory_format=_CL3)
+        gx = torch.empty((n, c, d, h, w), dtype=gy.dtype, device=gy.device, memory_format=_CL3)
+        with torch.cuda.device(gy.device):
+            L.check(lib.mdt_upsample221_backward(L.ptr(gy), L.ptr(gx), n, d, h, w, c, L.stream_ptr()))
+        return gx
+
+
 class Interpolate(nn.Module):
     def __init__(self, scale_factor, mode):
         super().__init__()
@@ -62,6 +89,9 @@ class Interpolate(nn.Module):
         self.mode = mode
 
     def forward(self, x):
+        if (x.is_cuda and x.dim() == 5 and x.dtype == torch.float32 and self.mode == 'trilinear' and tuple(self.scale_factor) == (2, 2, 1)
+                and x.shape[1] % 4 == 0):
+            return _Upsample221.apply(x)
         return F.interpolate(x, scale_factor=self.scale_factor, mode=self.mode, align_corners=False)
 
 
@@ -128,6 +158,14 @@ class FPN(nn.Module):
             self.P6_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
 
     @staticmethod
+    def _conv_plus(conv_mod, c, other):
+        """conv(c) + other with the add fused into the conv epilogue when conv_mod is a bare libmdt conv"""
+        if isinstance(conv_mod, Conv3d):
+            return _Conv3dFn.apply(c, conv_mod.weight, conv_mod.bias, _to_cl(other), conv_mod.stride, conv_mod.padding, False, conv_mod.precision,
+                                   conv_mod.algo)
+        return conv_mod(c) + other
+
+    @staticmethod
     def _lateral(conv_mod, c, top):
         """lateral 1x1 conv + nearest x2 upsampled coarser map, the add fused into the conv epilogue when possible"""
         up = F.interpolate(top, scale_factor=2)
@@ -160,8 +198,8 @@ class FPN(nn.Module):
         if self.sixth_pooling:
             outs.append(self.P6_conv2(p6_pre))
         if self.operate_stride1:
-            p1_pre = self.P1_conv1(c1) + self.P2_upsample(p2_pre)
-            p0_pre = self.P0_conv1(c0) + self.P1_upsample(p1_pre)
+            p1_pre = self._conv_plus(self.P1_conv1, c1, self.P2_upsample(p2_pre))
+            p0_pre = self._conv_plus(self.P0_conv1, c0, self.P1_upsample(p1_pre))
             # P1_conv2 exists (and is in the state dict) but is unused, as in the reference (backbone.py:175)
             outs = [self.P0_conv2(p0_pre)] + outs
         return outs

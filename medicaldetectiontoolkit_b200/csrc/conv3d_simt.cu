@@ -200,14 +200,25 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(ConvGeom g, const float *
         }
 }
 
-// db[co] = sum_m dy[m, co]
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ db, long long M, int cout,
+// db[co] = sum_m dy[m, co].  256 threads = (256 / cpad) row lanes x cpad channel lanes: coalesced row reads, shared-memory tree over the row
+// lanes, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ db, long long M, int cout, int cpad,
                                                        long long rows_per_block) {
+    __shared__ float red[256];
+    const int c = threadIdx.x % cpad, rl = threadIdx.x / cpad, nrl = 256 / cpad;
     const long long m0 = (long long)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+    for (int cb = 0; cb < cout; cb += cpad) {
         float s = 0.f;
-        for (long long m = m0; m < m1; ++m) s += __ldg(dy + m * cout + co);
-        atomicAdd(db + co, s);
+        if (cb + c < cout)
+            for (long long m = m0 + rl; m < m1; m += nrl) s += __ldg(dy + m * cout + cb + c);
+        red[threadIdx.x] = s;
+        __syncthreads();
+        if (rl == 0 && cb + c < cout) {
+            float t = 0.f;
+            for (int r = 0; r < nrl; ++r) t += red[r * cpad + c];
+            atomicAdd(db + cb + c, t);
+        }
+        __syncthreads();
     }
 }
 
@@ -240,10 +251,12 @@ int conv_bias_grad(const ConvGeom &g, const float *dy, float *db, cudaStream_t s
     const long long M = (long long)g.n * g.od * g.oh * g.ow;
     cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * g.cout, st);
     if (e != cudaSuccess) return (int)e;
-    long long blocks_ll = ceil_div<long long>(M, 512);
+    long long blocks_ll = ceil_div<long long>(M, 1024);
     if (blocks_ll > (long long)num_sms() * 8) blocks_ll = (long long)num_sms() * 8;
     const int blocks = (int)blocks_ll;
-    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, M, g.cout, ceil_div<long long>(M, blocks));
+    int cpad = 1;
+    while (cpad < g.cout && cpad < 64) cpad <<= 1;   // channel lanes per block (power of two <= 64)
+    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, M, g.cout, cpad, ceil_div<long long>(M, blocks));
     return launch_status();
 }
 

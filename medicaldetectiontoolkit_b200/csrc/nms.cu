@@ -118,6 +118,16 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
         const int base = b * kTile;
         const int size = min(n - base, kTile);
         const unsigned long long *dg = diag[b & 1];
+        // fast path: every box of this block is already suppressed -> nothing to resolve, nothing to OR (uniform branch: remv[b] is final here)
+        {
+            const unsigned long long all = size == kTile ? ~0ULL : ((1ULL << size) - 1ULL);
+            if ((remv[b] & all) == all) {
+                if (b + 1 < col_blocks && (int)threadIdx.x < kTile && base + kTile + (int)threadIdx.x < n)
+                    diag[(b + 1) & 1][threadIdx.x] = mask[(size_t)(base + kTile + threadIdx.x) * col_blocks + b + 1];
+                __syncthreads();
+                continue;
+            }
+        }
         if (threadIdx.x == 0) {
             unsigned long long rm = remv[b], kept = 0ULL;
             int cnt = s_count;

@@ -299,8 +299,8 @@ def refine_detections(rois, probs, deltas, batch_ixs, cf):
     kept[keep_pad.clamp(0, m - 1)[valid]] = True
     kept &= s_sorted >= 0
     n_b = int(batch_ixs.max().item()) + 1 if batch_ixs.numel() else 1
-    onehot = (b_sorted.unsqueeze(1) == torch.arange(n_b, device=dev).unsqueeze(0)) & kept.unsqueeze(1)
-    within = (torch.cumsum(onehot.long(), 0) * onehot).sum(1)
+    onehot = (b_sorted.unsqueeze(0) == torch.arange(n_b, device=dev).unsqueeze(1)) & kept.unsqueeze(0)   # [n_b, m]: scan along the contiguous dim
+    within = (torch.cumsum(onehot.to(torch.int32), 1) * onehot).sum(0)
     final = kept & (within <= cf.model_max_instances_per_batch_element)
     sel = torch.nonzero(final).squeeze(1)
     if sel.numel() == 0:   # the reference falls back to candidate 0 (mrcnn.py:706)

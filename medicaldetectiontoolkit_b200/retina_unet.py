@@ -161,9 +161,9 @@ def refine_detections(anchors, probs, deltas, batch_ixs, cf):
     kept[keep_pad.clamp(0, k - 1)[valid]] = True
     # top model_max_instances_per_batch_element per element, in score order
     n_b = int(batch_ixs.max().item()) + 1 if batch_ixs.numel() else 1
-    onehot = (b_ix.unsqueeze(1) == torch.arange(n_b, device=probs.device).unsqueeze(0)) & kept.unsqueeze(1)
-    rank = torch.cumsum(onehot.long(), 0)
-    within = (rank * onehot).sum(1)
+    onehot = (b_ix.unsqueeze(0) == torch.arange(n_b, device=probs.device).unsqueeze(1)) & kept.unsqueeze(0)   # [n_b, k]: scan along the contiguous dim
+    rank = torch.cumsum(onehot.to(torch.int32), 1)
+    within = (rank * onehot).sum(0)
     final = kept & (within <= cf.model_max_instances_per_batch_element)
     sel = torch.nonzero(final).squeeze(1)                                  # variable-length result: the one sync of the forward
     return torch.cat((rois[sel], b_ix[sel].unsqueeze(1).float(), class_ids[sel].unsqueeze(1).float(), scores[sel].unsqueeze(1)), dim=1)

@@ -182,3 +182,19 @@ def test_deconv2x_matches_conv_transpose():
     assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-4
 
     assert m.weight.grad is not None and torch.isfinite(m.weight.grad).all()
+
+
+def test_upsample221_matches_torch():
+    """csrc/resample.cu vs F.interpolate(scale (2,2,1), trilinear, align_corners=False), forward and backward (incl. edge clamping)"""
+    from medicaldetectiontoolkit_b200.backbone import Interpolate
+    torch.manual_seed(0)
+    for shape in [(2, 36, 5, 7, 6), (1, 8, 1, 1, 3), (1, 36, 16, 16, 16)]:
+        x = torch.randn(*shape, device=DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+        y = Interpolate((2, 2, 1), 'trilinear')(x)
+        xr = x.detach().double().requires_grad_(True)
+        yr = torch.nn.functional.interpolate(xr, scale_factor=(2, 2, 1), mode='trilinear', align_corners=False)
+        assert y.shape == yr.shape and _rel(y.detach().cpu().numpy(), yr.detach().cpu().numpy()) < 1e-6
+        g = torch.randn_like(y)
+        y.backward(g)
+        yr.backward(g.double())
+        assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-6
