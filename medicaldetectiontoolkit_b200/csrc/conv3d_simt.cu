@@ -200,25 +200,37 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt(ConvGeom g, const float *
         }
 }
 
-// db[co] = sum_m dy[m, co].  256 threads = (256 / cpad) row lanes x cpad channel lanes: coalesced row reads, shared-memory tree over the row
-// lanes, one atomicAdd per channel per block.
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ db, long long M, int cout, int cpad,
+// db[co] = sum_m dy[m, co].  dy is read as a FLAT array: the block walks it in strides of S = (256 / cout) * cout elements, so thread t always
+// owns channel t % cout and a warp's loads are 32 consecutive floats (fully coalesced, no idle channel lanes); 4 independent accumulators
+// keep 4 loads in flight per thread.  Shared-memory tree over the row lanes, one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ db, long long M, int cout,
                                                        long long rows_per_block) {
     __shared__ float red[256];
-    const int c = threadIdx.x % cpad, rl = threadIdx.x / cpad, nrl = 256 / cpad;
     const long long m0 = (long long)blockIdx.x * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    for (int cb = 0; cb < cout; cb += cpad) {
-        float s = 0.f;
-        if (cb + c < cout)
-            for (long long m = m0 + rl; m < m1; m += nrl) s += __ldg(dy + m * cout + cb + c);
-        red[threadIdx.x] = s;
-        __syncthreads();
-        if (rl == 0 && cb + c < cout) {
-            float t = 0.f;
-            for (int r = 0; r < nrl; ++r) t += red[r * cpad + c];
-            atomicAdd(db + cb + c, t);
+    if (cout <= 256) {
+        const int nrl = 256 / cout, active = nrl * cout;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if ((int)threadIdx.x < active) {
+            const long long e1 = m1 * cout;
+            long long e = m0 * cout + threadIdx.x;
+            for (; e + 3LL * active < e1; e += 4LL * active) {
+                s0 += __ldg(dy + e); s1 += __ldg(dy + e + active); s2 += __ldg(dy + e + 2LL * active); s3 += __ldg(dy + e + 3LL * active);
+            }
+            for (; e < e1; e += active) s0 += __ldg(dy + e);
         }
+        red[threadIdx.x] = (s0 + s1) + (s2 + s3);
         __syncthreads();
+        if ((int)threadIdx.x < cout) {
+            float t = 0.f;
+            for (int r = 0; r < nrl; ++r) t += red[r * cout + threadIdx.x];
+            atomicAdd(db + threadIdx.x, t);
+        }
+    } else {
+        for (int c = threadIdx.x; c < cout; c += 256) {
+            float s = 0.f;
+            for (long long m = m0; m < m1; ++m) s += __ldg(dy + m * cout + c);
+            atomicAdd(db + c, s);
+        }
     }
 }
 
@@ -254,9 +266,7 @@ int conv_bias_grad(const ConvGeom &g, const float *dy, float *db, cudaStream_t s
     long long blocks_ll = ceil_div<long long>(M, 1024);
     if (blocks_ll > (long long)num_sms() * 8) blocks_ll = (long long)num_sms() * 8;
     const int blocks = (int)blocks_ll;
-    int cpad = 1;
-    while (cpad < g.cout && cpad < 64) cpad <<= 1;   // channel lanes per block (power of two <= 64)
-    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, M, g.cout, cpad, ceil_div<long long>(M, blocks));
+    bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, M, g.cout, ceil_div<long long>(M, blocks));
     return launch_status();
 }
 
