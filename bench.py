@@ -79,7 +79,7 @@ def run_reference(args):
     import torch
     import cpu_step
     from medicaldetectiontoolkit_b200.configs import make_cf, synthetic_batch
-    cores = os.cpu_count() or 1
+    cores = cpu_step.calibrate_threads(os.cpu_count() or 1)
     torch.set_num_threads(cores)
     patch = tuple(args.patch)
     cf = make_cf('retina_unet', 3, patch)
@@ -255,7 +255,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import cpu_step
-        cores = os.cpu_count() or 1
+        cores = cpu_step.calibrate_threads(os.cpu_count() or 1)
         cb = synthetic_batch(cf, args.batch, seed=0)
         times, used = cpu_step.time_cpu_steps(cf, cb, steps=1, warmup=0, threads=cores)
         line["cpu_baseline"] = {"value": args.batch / times[0], "unit": "patches/s", "cores": used, "kind": "port",

@@ -145,6 +145,21 @@ def train_step_cpu(net, opt, cf, batch):
     return float(loss.item())
 
 
+def calibrate_threads(max_threads):
+    """torch's CPU conv3d does not scale to every hardware thread of a big host (128 threads ran 6x SLOWER than 8 on the same step):
+    time one small training step (64x64x32 patch) at a few thread counts and return the fastest — 'all the host threads it can use'."""
+    from medicaldetectiontoolkit_b200.configs import make_cf, synthetic_batch
+    cf = make_cf('retina_unet', 3, (64, 64, 32))
+    batch = synthetic_batch(cf, 1, seed=0)
+    best, best_t = None, None
+    cands = sorted(set(t for t in (8, 16, 32, 64, max_threads) if t <= max_threads))
+    for t in cands:
+        times, _ = time_cpu_steps(cf, batch, steps=1, warmup=0, threads=t)
+        if best_t is None or times[0] < best_t:
+            best, best_t = t, times[0]
+    return best
+
+
 def time_cpu_steps(cf, batch, steps=1, warmup=0, threads=None):
     """returns (seconds per step list, cores used)"""
     if threads:
