@@ -53,11 +53,32 @@ def _ev_end(e0, tag=None):
         EVENT_LOG.append((e0, e1, tag))
 
 
+_desc_cache = {}
+
+
 def _desc(x_shape, w_shape, stride, padding, relu, precision, algo):
-    n, cin, d, h, w = x_shape
-    cout, _, kd, kh, kw = w_shape
-    return L.Conv3dDesc(n, d, h, w, cin, cout, kd, kh, kw, stride[0], stride[1], stride[2], padding[0], padding[1], padding[2],
-                        int(bool(relu)), int(precision), int(algo))
+    key = (tuple(x_shape), tuple(w_shape), tuple(stride), tuple(padding), bool(relu), int(precision), int(algo))
+    d = _desc_cache.get(key)
+    if d is None:
+        n, cin, dd, h, w = x_shape
+        cout, _, kd, kh, kw = w_shape
+        d = L.Conv3dDesc(n, dd, h, w, cin, cout, kd, kh, kw, stride[0], stride[1], stride[2], padding[0], padding[1], padding[2],
+                         int(bool(relu)), int(precision), int(algo))
+        _desc_cache[key] = d
+    return d
+
+
+_plan_cache = {}
+
+
+def _plan(lib, d, ps):
+    """(workspace bytes, algorithm) of a descriptor/pass, cached: two ctypes calls saved per conv call"""
+    key = (id(d), ps)
+    v = _plan_cache.get(key)
+    if v is None:
+        v = (lib.mdt_conv3d_workspace_bytes(d, ps), lib.mdt_conv3d_algo(d, ps))
+        _plan_cache[key] = v
+    return v
 
 
 def _out_shape(x_shape, w_shape, stride, padding):
@@ -79,12 +100,11 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
     if residual is not None:
         residual = residual.contiguous(memory_format=_CL3)
     d = _desc(x.shape, w.shape, stride, padding, relu, precision, algo)
-    nbytes = lib.mdt_conv3d_workspace_bytes(d, 0)
+    nbytes, which = _plan(lib, d, 0)
     ws = _workspace(nbytes, x.device)
-    with torch.cuda.device(x.device):
-        ev = _ev_start()
-        L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), lib.mdt_conv3d_algo(d, 0)))
+    ev = _ev_start()
+    L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), which))
     return y
 
 
@@ -96,11 +116,11 @@ def conv3d_dgrad(dy, weight, x_shape, stride, padding, precision=None, algo=None
     w = weight.contiguous()
     dx = torch.empty(tuple(x_shape), dtype=torch.float32, device=dy.device, memory_format=_CL3)
     d = _desc(x_shape, w.shape, stride, padding, False, precision, algo)
-    ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 1), dy.device)
-    with torch.cuda.device(dy.device):
-        ev = _ev_start()
-        L.check(lib.mdt_conv3d_dgrad(d, L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev, (1, tuple(x_shape), tuple(w.shape), tuple(stride), lib.mdt_conv3d_algo(d, 1)))
+    nbytes, which = _plan(lib, d, 1)
+    ws = _workspace(nbytes, dy.device)
+    ev = _ev_start()
+    L.check(lib.mdt_conv3d_dgrad(d, L.ptr(dy), L.ptr(w), L.ptr(dx), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    _ev_end(ev, (1, tuple(x_shape), tuple(w.shape), tuple(stride), which))
     return dx
 
 
@@ -113,11 +133,11 @@ def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, alg
     dw = torch.empty(tuple(w_shape), dtype=torch.float32, device=x.device)
     db = torch.empty(w_shape[0], dtype=torch.float32, device=x.device) if want_bias else None
     d = _desc(x.shape, w_shape, stride, padding, False, precision, algo)
-    ws = _workspace(lib.mdt_conv3d_workspace_bytes(d, 2), x.device)
-    with torch.cuda.device(x.device):
-        ev = _ev_start()
-        L.check(lib.mdt_conv3d_wgrad(d, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()))
-        _ev_end(ev, (2, tuple(x.shape), tuple(w_shape), tuple(stride), lib.mdt_conv3d_algo(d, 2)))
+    nbytes, which = _plan(lib, d, 2)
+    ws = _workspace(nbytes, x.device)
+    ev = _ev_start()
+    L.check(lib.mdt_conv3d_wgrad(d, L.ptr(x), L.ptr(dy), L.ptr(dw), L.ptr(db), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    _ev_end(ev, (2, tuple(x.shape), tuple(w_shape), tuple(stride), which))
     return dw, db
 
 

@@ -134,7 +134,7 @@ __device__ __forceinline__ bool tc_step_coords(const TcConvParams &p, int rd, in
 // Split-bf16 uses N-stacking: the hi and lo weight planes of a tile are adjacent in shared memory, so  A_hi x [B_hi ; B_lo]  is ONE
 // MMA with N = 2*NT (accumulator columns [0,NT) += hi*hi, [NT,2NT) += hi*lo) followed by  A_lo x B_hi  (N = NT); the epilogue adds the
 // two column halves.  2 MMAs and 2 A reads per K step instead of 3.
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 5)   // <= 68 registers: residency (CTAs per SM) is what hides the per-stage latency
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t full[kTcMaxStages], empty[kTcMaxStages], accum_full;
@@ -417,8 +417,9 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     stage = bytes(CPS, TPS);
     // Measured on B200 (profiles/r01_mma_rate.txt, r01_stage_sweep.txt): one thread cannot issue tcgen05.mma faster than ~60 cycles each, so for
     // the small N of these layers a single CTA leaves the tensor pipe idle; co-resident CTAs fill it.  Residency beats ring depth: keep the
-    // footprint minimal (1 stage when a stage is large, 2 when small) so that 2-4 CTAs share an SM and overlap each other's loads/epilogues.
-    D = stage > 40 * 1024 ? 1 : 2;
+    // footprint minimal (ONE stage, <= 64 registers/thread) so that 2-5 CTAs share an SM and overlap each other's loads, MMAs and epilogues
+    // (sweep over D in {1,2} x taps-per-stage in profiles/r01_stage_sweep.txt: D = 1 with all kw taps per stage wins on every hot layer).
+    D = 1;
     if (const char *e = getenv("MDT_TC_D")) { const int v = atoi(e); if (v >= 1 && v <= kTcMaxStages && v * stage <= budget) D = v; }
     return true;
 }

@@ -111,23 +111,30 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
     __shared__ int s_count;
     for (int j = threadIdx.x; j < col_blocks; j += kScanThreads) remv[j] = 0ULL;
     if (threadIdx.x == 0) s_count = 0;
-    if ((int)threadIdx.x < min(n, kTile)) diag[0][threadIdx.x] = mask[(size_t)threadIdx.x * col_blocks];
     __syncthreads();
     const int r = threadIdx.x / kScanLanes, l = threadIdx.x % kScanLanes;
-    for (int b = 0; b < col_blocks; ++b) {
+    __shared__ int s_next;
+    int b = 0;
+    while (b < col_blocks) {
+        // skip ahead over blocks whose boxes are all suppressed already (remv[b..] is final for them: only kept boxes ever add bits):
+        // one thread walks the shared-memory bitmap, no global access, one barrier per RUN of skipped blocks
+        if (threadIdx.x == 0) {
+            int nb = b;
+            while (nb < col_blocks) {
+                const int sz = min(n - nb * kTile, kTile);
+                const unsigned long long all = sz == kTile ? ~0ULL : ((1ULL << sz) - 1ULL);
+                if ((remv[nb] & all) != all) break;
+                ++nb;
+            }
+            s_next = nb;
+        }
+        __syncthreads();
+        b = s_next;
+        if (b >= col_blocks) break;
         const int base = b * kTile;
         const int size = min(n - base, kTile);
-        const unsigned long long *dg = diag[b & 1];
-        // fast path: every box of this block is already suppressed -> nothing to resolve, nothing to OR (uniform branch: remv[b] is final here)
-        {
-            const unsigned long long all = size == kTile ? ~0ULL : ((1ULL << size) - 1ULL);
-            if ((remv[b] & all) == all) {
-                if (b + 1 < col_blocks && (int)threadIdx.x < kTile && base + kTile + (int)threadIdx.x < n)
-                    diag[(b + 1) & 1][threadIdx.x] = mask[(size_t)(base + kTile + threadIdx.x) * col_blocks + b + 1];
-                __syncthreads();
-                continue;
-            }
-        }
+        if ((int)threadIdx.x < size) diag[0][threadIdx.x] = mask[(size_t)(base + threadIdx.x) * col_blocks + b];
+        __syncthreads();
         if (threadIdx.x == 0) {
             unsigned long long rm = remv[b], kept = 0ULL;
             int cnt = s_count;
@@ -135,16 +142,11 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
                 if (!((rm >> i) & 1ULL)) {
                     kept |= 1ULL << i;
                     keep[cnt++] = base + i;
-                    rm |= dg[i];
+                    rm |= diag[0][i];
                 }
             }
             s_kept = kept;
             s_count = cnt;
-        }
-        // prefetch the next block's diagonal words (independent of remv)
-        if (b + 1 < col_blocks && (int)threadIdx.x >= kScanThreads - kTile) {
-            const int i = threadIdx.x - (kScanThreads - kTile);
-            if (base + kTile + i < n) diag[(b + 1) & 1][i] = mask[(size_t)(base + kTile + i) * col_blocks + b + 1];
         }
         __syncthreads();
         if ((s_kept >> r) & 1ULL) {
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
             }
         }
         __syncthreads();
+        ++b;
     }
     if (threadIdx.x == 0) *num_out = s_count;
 }
