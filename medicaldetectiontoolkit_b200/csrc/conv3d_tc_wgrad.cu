@@ -15,6 +15,7 @@
 // dw with fp32 red.global.add.
 #include "conv3d_common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace mdt {
 using namespace tc;
@@ -30,7 +31,7 @@ struct TcWgradParams {
     int mtrick;
     int swx, chunkx, nxc;            // x: swizzle bytes, channels per chunk, number of ci chunks
     int ncb_total, CB, groups, splits;
-    int planes;
+    int planes, stages, tmem_cols;
     int y_chunk_bytes, y_plane_bytes, x_plane_bytes, x_buf_bytes, stage_bytes;
     int y_tx_bytes, x_tx_bytes;      // bytes one TMA box delivers
     long long units;                 // NB * OD * OH * segs
@@ -39,7 +40,7 @@ struct TcWgradParams {
 };
 
 constexpr int kWgThreads = 192;
-constexpr int kWgStages = 2;
+constexpr int kWgMaxStages = 2;
 
 __device__ __forceinline__ void wg_decode_cb(const TcWgradParams &p, int cb, int &kd, int &kh, int &xc) {
     xc = cb % p.nxc;
@@ -51,7 +52,7 @@ __device__ __forceinline__ void wg_decode_cb(const TcWgradParams &p, int cb, int
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcWgradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t full[kWgStages], empty[kWgStages], accum_full;
+    __shared__ uint64_t full[kWgMaxStages], empty[kWgMaxStages], accum_full;
     __shared__ uint32_t tmem_base_s, s_started;
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -63,14 +64,14 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     const int ncols = p.KW * p.chunkx;               // accumulator columns per column block
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWgStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(&accum_full, 1);
         s_started = 0;
         fence_barrier_init();
         prefetch_tmap(&tmY);
         prefetch_tmap(&tmX);
     }
-    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    if (warp == 1) tmem_alloc(&tmem_base_s, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -91,8 +92,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
             for (long long u = split; u < p.units; u += p.splits, ++it) {
                 int n, od, oh, ow0;
                 decode_unit(u, n, od, oh, ow0);
-                const int s = it % kWgStages;
-                mbar_wait(&empty[s], ((it / kWgStages) & 1) ^ 1);
+                const int s = it % p.stages;
+                mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
                 uint8_t *st = smem + (size_t)s * p.stage_bytes;
                 // which column blocks have their source line inside the image
                 uint32_t bytes = p.planes * p.nmc * p.y_tx_bytes;
@@ -131,8 +132,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
             for (long long u = split; u < p.units; u += p.splits, ++it) {
                 int n, od, oh, ow0;
                 decode_unit(u, n, od, oh, ow0);
-                const int s = it % kWgStages;
-                mbar_wait(&full[s], (it / kWgStages) & 1);
+                const int s = it % p.stages;
+                mbar_wait(&full[s], (it / p.stages) & 1);
                 tc_fence_after();
                 const uint32_t y_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
                 const uint32_t x0 = y_hi + p.planes * p.y_plane_bytes;
@@ -198,7 +199,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 512);
+    if (warp == 1) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // dw[co, ci, tap] = sum over splits (and over the hi / lo lane halves in mtrick mode) of the partial accumulators
@@ -231,7 +232,7 @@ struct WgPlan {
     int co_p, swy, chunky, nmc, mtiles, mtrick;
     int ci_p, swx, chunkx, nxc;
     int seg, segs, ksteps, rows_y, rows_x, rows_x_pad;
-    int ncb_total, CB, groups;
+    int ncb_total, CB, groups, stages, waves;
 };
 
 static WgPlan make_wg_plan(const ConvGeom &g) {
@@ -266,10 +267,19 @@ static WgPlan make_wg_plan(const ConvGeom &g) {
     w.CB = 512 / (g.kw * w.chunkx);
     if (w.CB > 32) w.CB = 32;
     if (w.CB > w.ncb_total) w.CB = w.ncb_total;
+    // Narrow x operands (<= 32 channels: small N per MMA, issue-bound) run best as many small co-resident CTAs — one column block and a
+    // small TMEM/shared-memory footprint each; wide ones (64-channel chunks, tensor-bound N = kw*64) as one big CTA per SM.  Measured sweep:
+    // profiles/r01_wgrad_sweep.txt.
+    w.waves = 1;
+    if (w.chunkx <= 32) { w.CB = 1; w.waves = 2; }
+    if (const char *e = getenv("MDT_WG_CB")) { const int v = atoi(e); if (v >= 1 && v < w.CB) w.CB = v; }   // experiment knobs
+    if (const char *e = getenv("MDT_WG_WAVES")) { const int v = atoi(e); if (v >= 1 && v <= 8) w.waves = v; }
     // shared memory: 2 stages of (dy planes + CB x buffers)
     auto stage_bytes = [&](int cb, int planes) { return planes * w.nmc * w.rows_y * w.swy + cb * planes * w.rows_x_pad * w.swx; };
-    while (w.CB > 1 && kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) --w.CB;
-    if (kWgStages * stage_bytes(w.CB, 2) > 200 * 1024) return w;
+    w.stages = kWgMaxStages;
+    if (const char *e = getenv("MDT_WG_STAGES")) { const int v = atoi(e); if (v >= 1 && v <= kWgMaxStages) w.stages = v; }
+    while (w.CB > 1 && w.stages * stage_bytes(w.CB, 2) > 200 * 1024) --w.CB;
+    if (w.stages * stage_bytes(w.CB, 2) > 200 * 1024) return w;
     w.groups = ceil_div(w.ncb_total, w.CB);
     w.ok = true;
     return w;
@@ -282,7 +292,7 @@ static size_t wg_align(size_t v) { return (v + 1023) / 1024 * 1024; }
 // split-K factor: one full wave of CTAs (1 CTA per SM: the kernel uses most of the shared memory)
 static int wg_splits(const ConvGeom &g, const WgPlan &w) {
     const long long units = (long long)g.n * g.od * g.oh * w.segs;
-    long long splits = (long long)num_sms() / ((long long)w.groups * w.mtiles);
+    long long splits = (long long)num_sms() * w.waves / ((long long)w.groups * w.mtiles);   // w.waves CTAs per SM, co-resident
     if (splits < 1) splits = 1;
     if (splits > units) splits = units;
     return (int)splits;
@@ -327,6 +337,9 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     p.swx = w.swx; p.chunkx = w.chunkx; p.nxc = w.nxc;
     p.ncb_total = w.ncb_total; p.CB = w.CB; p.groups = w.groups;
     p.planes = planes;
+    p.stages = w.stages;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < w.CB * g.kw * w.chunkx) p.tmem_cols <<= 1;
     p.y_chunk_bytes = w.rows_y * w.swy;
     p.y_plane_bytes = w.nmc * p.y_chunk_bytes;
     p.x_plane_bytes = w.rows_x_pad * w.swx;
@@ -356,7 +369,7 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     // epilogue); make sure that walk stays inside the allocation for the last stage too
     const size_t walk = (size_t)(128 / w.chunky) * w.rows_y * w.swy;
     const size_t tail = walk > (size_t)p.stage_bytes ? walk - p.stage_bytes : 0;
-    const size_t smem = (size_t)kWgStages * p.stage_bytes + 1024 + tail;
+    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + tail;
     if (smem > 218 * 1024) return MDT_EUNSUPPORTED;
     static bool attr = false;
     if (!attr) {
