@@ -198,3 +198,45 @@ def test_upsample221_matches_torch():
         y.backward(g)
         yr.backward(g.double())
         assert _rel(x.grad.cpu().numpy(), xr.grad.cpu().numpy()) < 1e-6
+
+
+def _copy_state(dst, src):
+    """load the CPU port's stock-torch weights into our modules: identical key sets are part of the check"""
+    sd_src = {k: v for k, v in src.state_dict().items()}
+    sd_dst = dst.state_dict()
+    assert sorted(sd_src) == sorted(sd_dst), (sorted(set(sd_src) ^ set(sd_dst)))
+    dst.load_state_dict(sd_src)
+
+
+@pytest.mark.parametrize("dim,patch", [(3, (64, 64, 32)), (2, (128, 128))])
+def test_retina_forward_matches_cpu_port(dim, patch):
+    """Model-level parity: our Retina U-Net (3D) / RetinaNet-style heads (2D, the toy_exp plumbing config) on the GPU kernels vs the same graph
+    built from stock torch.nn.Conv{2,3}d on the CPU (oracle/cpu_step.py), identical weights: class logits, box deltas, seg logits to 1e-4."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_step
+    from medicaldetectiontoolkit_b200 import retina_unet
+    cf = make_cf('retina_unet', dim, patch, exp='toy_exp' if dim == 2 else 'lidc_exp')
+    torch.manual_seed(5)
+    ref = cpu_step.build_cpu_net(cf).float()
+    net = retina_unet.net(cf, None)
+    _copy_state(net, ref)
+    net = net.to(DEV)
+    x = torch.from_numpy(np.random.RandomState(1).rand(2, 1, *patch).astype(np.float32))
+    with torch.no_grad():
+        cl_r, bb_r, seg_r = ref(x)
+        det, cl, bb, seg = net(x.to(DEV))
+    assert cl.shape == cl_r.shape and bb.shape == bb_r.shape and seg.shape == seg_r.shape
+    assert _rel(cl.cpu().numpy(), cl_r.numpy()) < 1e-4
+    assert _rel(bb.cpu().numpy(), bb_r.numpy()) < 1e-4
+    assert _rel(seg.cpu().numpy(), seg_r.numpy()) < 1e-4
+    assert det.shape[1] == 2 * dim + 3 and det.shape[0] <= 2 * cf.model_max_instances_per_batch_element
+    # detections of the GPU path == the host restatement of refine_detections (retina_unet.py:194-271) on the reference logits
+    import torch.nn.functional as F
+    B, A = cl_r.shape[0], cl_r.shape[1]
+    batch_ixs = torch.arange(B).unsqueeze(1).repeat(1, A).view(-1)
+    det_r = cpu_step.refine_detections_cpu(cf, ref.anchors, F.softmax(cl.cpu().view(-1, cl.shape[-1]), 1), bb.cpu().view(-1, bb.shape[-1]), batch_ixs)
+    got = det.cpu()
+    assert got.shape == det_r.shape
+    order_g = np.lexsort((got[:, -1].numpy(), got[:, 2 * dim].numpy()))
+    order_r = np.lexsort((det_r[:, -1].numpy(), det_r[:, 2 * dim].numpy()))
+    assert np.allclose(got.numpy()[order_g], det_r.numpy()[order_r], atol=1e-5)
