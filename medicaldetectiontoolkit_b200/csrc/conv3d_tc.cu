@@ -171,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int acc1_cols = p.planes > 1 ? 2 * p.NT : p.NT;
     const int Q = p.Q;
     const int acc2_base = Q * acc1_cols;
-    const int acc_total = acc2_base + (p.planes > 1 ? Q * p.NT : 0);
+    const int acc_total = acc2_base;   // no separate type-2 accumulators: keeps TMEM at 2*NT columns so that up to 4 CTAs fit in the SM's 512
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < acc_total) tmem_cols <<= 1;
     if (warp == 1) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -194,7 +194,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int kw0 = 0; kw0 < p.KW; kw0 += p.TPS) {
                             mbar_wait(&empty[s], ph);
                             uint8_t *st = smem + (size_t)s * p.stage_bytes;
-                            mbar_arrive_expect_tx(&full[s], (uint32_t)(cn * p.planes * (p.a_tx_bytes + p.TPS * p.b_plane_bytes)));
+                            // halo mode, single stage: the A halo of this (kd, kh, chunk group) is fetched with the FIRST tap group only and stays
+                            // in place while the later tap groups stream their weight tiles through the B area
+                            const bool load_a = !(p.halo && p.D == 1) || kw0 == 0;
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)(cn * p.planes * ((load_a ? p.a_tx_bytes : 0) + p.TPS * p.b_plane_bytes)));
                             int w_start;
                             if (p.halo) w_start = p.dgrad ? rw0 + p.pw - (p.KW - 1) : rw0 - p.pw;
                             else        w_start = p.dgrad ? rw0 + p.pw - kw0 : rw0 - p.pw + kw0;
@@ -202,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int c = 0; c < cn; ++c) {
                                 uint8_t *ab = st + (size_t)c * p.a_chunk_bytes;
                                 if (p.halo) {   // one box = both planes of the halo line: {chunk, voxels, planes, 1, 1}
-                                    tma_load_5d(ab, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start, 0, h_src, nb * p.SD + d_src);
+                                    if (load_a) tma_load_5d(ab, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start, 0, h_src, nb * p.SD + d_src);
                                 } else {
                                     for (int pl = 0; pl < p.planes; ++pl)
                                         tma_load_5d(ab + (size_t)pl * p.a_plane_bytes, &tmA, &full[s], (c_lo + c) * chunk_elems, w_start, pl, h_src,
@@ -232,7 +235,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int s = 0;
             uint32_t ph = 0;
             uint32_t n1 = 0, n2 = 0;          // MMAs issued per type
-            uint32_t q1 = 0, q2 = 0;          // round-robin cursors
+            uint32_t q1 = 0;                  // round-robin cursor
             for (int kd = 0; kd < p.KD; ++kd)
                 for (int kh = 0; kh < p.KH; ++kh) {
                     int d_src, h_src;
@@ -254,13 +257,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     uint64_t dal = dtmpl | (uint64_t)(((a_hi + p.a_plane_bytes) >> 4) & 0x3FFF);
                                     for (int j = 0; j < ksteps; ++j) {
                                         umma_bf16(tmem + q1 * acc1_cols, da, db, p.planes > 1 ? idesc2 : idesc1, n1 >= (uint32_t)Q);
+                                        const uint32_t qprev = q1;
                                         ++n1;
                                         if (++q1 == (uint32_t)Q) q1 = 0;
-                                        if (p.planes > 1) {
-                                            umma_bf16(tmem + acc2_base + q2 * p.NT, dal, db, idesc1, n2 >= (uint32_t)Q);
-                                            ++n2;
-                                            if (++q2 == (uint32_t)Q) q2 = 0;
-                                        }
+                                        if (p.planes > 1)   // A_lo x B_hi accumulates into the hi*hi columns of the same accumulator (in-order after MMA 1)
+                                            umma_bf16(tmem + qprev * acc1_cols, dal, db, idesc1, 1);
                                         da += 2; db += 2; dal += 2;          // +32 bytes along K
                                     }
                                 }
@@ -375,11 +376,13 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
     // K padding: one swizzle-span chunk for <= 64 channels (few, large TMA boxes), 64-channel chunks above
     pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;
+    static const bool k16 = getenv("MDT_TC_K16") != nullptr;   // experiment: pad K to 16 only (more, smaller TMA boxes; fewer K steps)
+    if (k16) pl.Kp = ceil_div(pl.Kc, 16) * 16;
     pl.Np = ceil_div(pl.Nc, 16) * 16;
     pl.NT = pl.Np <= 128 ? pl.Np : 128;
     pl.n_tiles_n = ceil_div(pl.Np, pl.NT);
     if (pl.Np % pl.NT) pl.Np = pl.n_tiles_n * pl.NT;   // keep the TMA box inside the packed weight tensor
-    pl.swz = pl.Kp >= 64 ? 128 : pl.Kp * 2;
+    pl.swz = (pl.Kp % 64 == 0) ? 128 : (pl.Kp % 32 == 0) ? 64 : 32;
     pl.nchunks = pl.Kp / (pl.swz / 2);
     if (pl.RW >= 128) { pl.BW = 128; pl.BH = 1; }
     else {
@@ -412,6 +415,8 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     while (CPS > 1 && 3 * bytes(CPS, TPS) > budget) --CPS;
     while (TPS > 1 && 2 * bytes(CPS, TPS) > budget) --TPS;
     if (2 * bytes(CPS, TPS) > budget) return false;
+    // single-stage halo mode keeps A in place across tap groups, so a smaller tap group costs no extra traffic: shrink it until 4 CTAs fit
+    if (pl.halo) while (TPS > 1 && bytes(CPS, TPS) > 54 * 1024) --TPS;
     // experiment knobs (tools/conv_layer_bench.py): MDT_TC_TPS caps the taps per stage, MDT_TC_D sets the ring depth
     if (const char *e = getenv("MDT_TC_TPS")) { const int v = atoi(e); if (v >= 1 && v < TPS) TPS = v; }
     stage = bytes(CPS, TPS);
