@@ -123,6 +123,14 @@ int mdt_conv3d_dgrad(const mdt_conv3d_desc *desc_host, const float *dy, const fl
 /* dw = x (*) dy ; db = sum(dy) (db may be NULL) */
 int mdt_conv3d_wgrad(const mdt_conv3d_desc *desc_host, const float *x, const float *dy, float *dw, float *db, void *workspace,
                      size_t workspace_bytes, void *stream);
+/* Fused backward of one conv layer (tcgen05 path): ONE streaming pass over dy yields the split-bf16 operand shared by dgrad and wgrad, applies
+ * the ReLU mask of a fused-ReLU conv (y_relu = its forward output, NULL = no mask; replaces aten::threshold_backward of the reference graph),
+ * accumulates db, and optionally writes the masked fp32 gradient (dy_masked_out, needed as the gradient of a fused residual input).
+ * dx may be NULL (first layer).  mdt_conv3d_backward_fused() tells whether this path applies; otherwise use dgrad + wgrad. */
+int mdt_conv3d_backward_fused(const mdt_conv3d_desc *desc_host, int need_dx);
+size_t mdt_conv3d_backward_workspace_bytes(const mdt_conv3d_desc *desc_host, int need_dx);
+int mdt_conv3d_backward(const mdt_conv3d_desc *desc_host, const float *x, const float *dy, const float *y_relu, const float *w, float *dx,
+                        float *dw, float *db, float *dy_masked_out, void *workspace, size_t workspace_bytes, void *stream);
 /* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
 /* ------------------------------------------------------------- decoder up-sampling -----------------------------------------------------------

@@ -141,6 +141,39 @@ def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, alg
     return dw, db
 
 
+_bwd_plan_cache = {}
+
+
+def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, want_masked, precision=None, algo=None):
+    """Fused backward of one conv (see mdt_conv3d_backward in include/mdt_b200.h).  Returns (dx|None, dw, db|None, gy_masked|None), or None when
+    the fused tcgen05 path does not apply to this shape (caller then runs mask + dgrad + wgrad separately)."""
+    lib = L.load()
+    precision = DEFAULT_PRECISION if precision is None else precision
+    algo = DEFAULT_ALGO if algo is None else algo
+    d = _desc(x.shape, weight.shape, stride, padding, False, precision, algo)
+    key = (id(d), bool(need_dx))
+    plan = _bwd_plan_cache.get(key)
+    if plan is None:
+        plan = (lib.mdt_conv3d_backward_fused(d, int(need_dx)), lib.mdt_conv3d_backward_workspace_bytes(d, int(need_dx)))
+        _bwd_plan_cache[key] = plan
+    if not plan[0]:
+        return None
+    x = x.contiguous(memory_format=_CL3)
+    gy = gy.contiguous(memory_format=_CL3)
+    w = weight.contiguous()
+    dev = x.device
+    dx = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev, memory_format=_CL3) if need_dx else None
+    dw = torch.empty(tuple(w.shape), dtype=torch.float32, device=dev)
+    db = torch.empty(w.shape[0], dtype=torch.float32, device=dev) if want_bias else None
+    gm = torch.empty_like(gy) if want_masked else None
+    ws = _workspace(plan[1], dev)
+    ev = _ev_start()
+    L.check(lib.mdt_conv3d_backward(d, L.ptr(x), L.ptr(gy), L.ptr(y_relu), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(gm), L.ptr(ws),
+                                    ws.numel(), L.stream_ptr()))
+    _ev_end(ev, (3, tuple(x.shape), tuple(w.shape), tuple(stride), 2))
+    return dx, dw, db, gm
+
+
 class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, stride, padding, relu, precision, algo):
@@ -154,6 +187,14 @@ class _Conv3dFn(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         stride, padding, relu, precision, algo, x_shape, has_bias, has_res = ctx.cfg
         gy = gy.contiguous(memory_format=_CL3)
+        need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
+        if need_w:
+            want_masked = has_res and ctx.needs_input_grad[3] and relu
+            fused = conv3d_backward(x, gy, y if relu else None, weight, stride, padding, ctx.needs_input_grad[0], has_bias, want_masked, precision, algo)
+            if fused is not None:
+                gx, gw, gb, gm = fused
+                gres = (gm if relu else gy) if (has_res and ctx.needs_input_grad[3]) else None
+                return gx, gw, gb, gres, None, None, None, None, None
         if relu:
             gy = torch.ops.aten.threshold_backward(gy, y, 0.0)  # ReLU mask (elementwise, HBM-bound)
         gx = gw = gb = None

@@ -60,4 +60,27 @@ int mdt_conv3d_wgrad(const mdt_conv3d_desc *c, const float *x, const float *dy, 
     return mdt::conv_simt_wgrad(g, x, dy, dw, db, mdt::as_stream(stream));
 }
 
+/* fused backward: 1 if the tcgen05 fused path (one pass over dy shared by dgrad + wgrad, ReLU mask and bias gradient folded in) applies */
+int mdt_conv3d_backward_fused(const mdt_conv3d_desc *c, int need_dx) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g)) return 0;
+    if (c->algo == 1) return 0;
+    return mdt::conv_tc_backward_supported(g, need_dx != 0) ? 1 : 0;
+}
+
+size_t mdt_conv3d_backward_workspace_bytes(const mdt_conv3d_desc *c, int need_dx) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g)) return 0;
+    return mdt::conv_tc_backward_workspace_bytes(g, need_dx != 0, c->precision) + 256;
+}
+
+int mdt_conv3d_backward(const mdt_conv3d_desc *c, const float *x, const float *dy, const float *y_relu, const float *w, float *dx, float *dw,
+                        float *db, float *dy_masked_out, void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x || !dy || !w || !dw) return MDT_EINVAL;
+    if (!mdt_conv3d_backward_fused(c, dx != nullptr)) return MDT_EUNSUPPORTED;
+    if (!ws || ws_bytes < mdt_conv3d_backward_workspace_bytes(c, dx != nullptr)) return MDT_EWORKSPACE;
+    return mdt::conv_tc_backward(g, x, dy, y_relu, w, dx, dw, db, dy_masked_out, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+}
+
 }  // extern "C"

@@ -38,4 +38,10 @@ int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx,
 int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
                   cudaStream_t st);
 
+// fused backward (conv3d_tc_wgrad.cu)
+bool conv_tc_backward_supported(const ConvGeom &g, bool need_dx);
+size_t conv_tc_backward_workspace_bytes(const ConvGeom &g, bool need_dx, int precision);
+int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const float *relu_of, const float *w, float *dx, float *dw, float *db,
+                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st);
+
 }  // namespace mdt

@@ -32,16 +32,40 @@ using namespace tc;
 //   inter_w > 0: line-interleaved [line][plane][inter_w voxels][Cp]   (fprop/dgrad A operand: both planes of a W-line are adjacent, so ONE
 //                TMA box {chunk, voxels, 2 planes} fetches the hi and lo halo line together); rows = lines * inter_w
 __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C,
-                                                        int Cp, int planes, int inter_w) {
+                                                        int Cp, int planes, int inter_w, const float *__restrict__ relu_of,
+                                                        float *__restrict__ masked_out, float *__restrict__ colsum) {
+    // backward-pass extras, all fused into this one streaming pass over dy:
+    //   relu_of    : forward output y of a conv with fused ReLU -> the element is zeroed where y <= 0 (threshold_backward)
+    //   masked_out : fp32 copy of the masked gradient (needed when it is also the gradient of a fused residual input)
+    //   colsum     : [C] bias gradient, accumulated per block in shared memory, one global atomic per channel and block
+    __shared__ float s_sum[256];
     const int groups = Cp / 8;  // 8 channels (16 bytes of bf16) per thread
     const long long total = rows * groups;
     const long long plane_stride = inter_w > 0 ? (long long)inter_w * Cp : rows * Cp;
+    if (colsum) {
+        for (int i = threadIdx.x; i < Cp && i < 256; i += blockDim.x) s_sum[i] = 0.f;
+        __syncthreads();
+    }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long r = i / groups;
         const int c0 = (int)(i % groups) * 8;
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (c0 + k < C) ? __ldg(src + r * C + c0 + k) : 0.f;
+        for (int k = 0; k < 8; ++k) {
+            float t = (c0 + k < C) ? __ldg(src + r * C + c0 + k) : 0.f;
+            if (relu_of && c0 + k < C && !(__ldg(relu_of + r * C + c0 + k) > 0.f)) t = 0.f;
+            v[k] = t;
+        }
+        if (masked_out) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + k < C) masked_out[r * C + c0 + k] = v[k];
+        }
+        if (colsum) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (c0 + k < C && v[k] != 0.f) atomicAdd(&s_sum[c0 + k], v[k]);
+        }
         __align__(16) __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -53,6 +77,11 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
         else off = r * Cp + c0;
         *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(hi);
         if (planes > 1) *reinterpret_cast<uint4 *>(dst + off + plane_stride) = *reinterpret_cast<const uint4 *>(lo);
+    }
+    if (colsum) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < C && i < 256; i += blockDim.x)
+            if (s_sum[i] != 0.f) atomicAdd(colsum + i, s_sum[i]);
     }
 }
 
@@ -375,9 +404,7 @@ static TcPlan make_plan(const ConvGeom &g, int pass) {
     pl.RD = dgrad ? g.d : g.od; pl.RH = dgrad ? g.h : g.oh; pl.RW = dgrad ? g.w : g.ow;
     pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
     // K padding: one swizzle-span chunk for <= 64 channels (few, large TMA boxes), 64-channel chunks above
-    pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;
-    static const bool k16 = getenv("MDT_TC_K16") != nullptr;   // experiment: pad K to 16 only (more, smaller TMA boxes; fewer K steps)
-    if (k16) pl.Kp = ceil_div(pl.Kc, 16) * 16;
+    pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;   // == conv_tc_kpad(); padding to 16 only was measured 24 % slower
     pl.Np = ceil_div(pl.Nc, 16) * 16;
     pl.NT = pl.Np <= 128 ? pl.Np : 128;
     pl.n_tiles_n = ceil_div(pl.Np, pl.NT);
@@ -429,6 +456,8 @@ static bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, int &TPS
     return true;
 }
 
+int conv_tc_kpad(int channels) { return channels <= 16 ? 16 : channels <= 32 ? 32 : ceil_div(channels, 64) * 64; }
+
 bool conv_tc_wgrad_supported(const ConvGeom &g);
 size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision);
 
@@ -456,8 +485,9 @@ size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
     return align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024) + align_up((size_t)weight_reps(pl, T, planes) * planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
 }
 
-static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
-                       int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+// presplit != nullptr: the A operand is already in split form (layout of split_rows_kernel with inter_w = SW) and `src` is ignored
+int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
+                int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit) {
     const TcPlan pl = make_plan(g, pass);
     if (!pl.ok) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_workspace_bytes(g, pass, precision)) return MDT_EWORKSPACE;
@@ -465,14 +495,14 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
     const int T = g.kd * g.kh * g.kw;
     const bool dgrad = pass == 1;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
-    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *xs = presplit ? const_cast<__nv_bfloat16 *>(presplit) : reinterpret_cast<__nv_bfloat16 *>(base);
     __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024));
 
     {   // operand preparation
         const long long total = pl.src_rows * (pl.Kp / 8);
         long long blocks = ceil_div<long long>(total, 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes, pl.SW);
+        if (!presplit) split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes, pl.SW, nullptr, nullptr, nullptr);
         int rc = launch_status();
         if (rc) return rc;
         const long long wt = (long long)T * pl.Np * pl.Kp;
@@ -526,10 +556,10 @@ static int conv_tc_run(const ConvGeom &g, int pass, const float *src, const floa
 
 int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
                   void *ws, size_t ws_bytes, cudaStream_t st) {
-    return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st);
+    return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st, nullptr);
 }
 int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
-    return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st);
+    return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st, nullptr);
 }
 
 }  // namespace mdt

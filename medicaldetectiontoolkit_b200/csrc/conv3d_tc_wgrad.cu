@@ -20,7 +20,12 @@
 namespace mdt {
 using namespace tc;
 
-__global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes, int inter_w);
+__global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes, int inter_w,
+                                  const float *__restrict__ relu_of, float *__restrict__ masked_out, float *__restrict__ colsum);
+int conv_tc_kpad(int channels);
+int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst, int relu,
+                int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit);
+size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
 
 struct TcWgradParams {
     int NB, OD, OH, OW, D, H, W;
@@ -107,7 +112,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 for (int pl = 0; pl < p.planes; ++pl)
                     for (int mc = 0; mc < p.nmc; ++mc)
                         tma_load_5d(st + (size_t)pl * p.y_plane_bytes + (size_t)mc * p.y_chunk_bytes, &tmY, &full[s], (mt * p.nmc + mc) * p.chunky, ow0,
-                                    oh, od, n + pl * p.NB);
+                                    pl, oh, n * p.OD + od);
                 uint8_t *xb = st + (size_t)p.planes * p.y_plane_bytes;
                 for (int b = 0; b < ncb; ++b) {
                     int kd, kh, xc;
@@ -115,8 +120,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                     const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
                     if (d < 0 || d >= p.D || h < 0 || h >= p.H) continue;
                     for (int pl = 0; pl < p.planes; ++pl)
-                        tma_load_5d(xb + (size_t)b * p.x_buf_bytes + (size_t)pl * p.x_plane_bytes, &tmX, &full[s], xc * p.chunkx, ow0 - p.pw, h, d,
-                                    n + pl * p.NB);
+                        tma_load_5d(xb + (size_t)b * p.x_buf_bytes + (size_t)pl * p.x_plane_bytes, &tmX, &full[s], xc * p.chunkx, ow0 - p.pw, pl, h,
+                                    n * p.D + d);
                 }
             }
         }
@@ -239,22 +244,21 @@ static WgPlan make_wg_plan(const ConvGeom &g) {
     WgPlan w;
     if (g.sw != 1) return w;
     // x (N side): one chunk spans all of ci when ci <= 64, so that all kw taps of a pair fit one MMA
-    w.ci_p = g.cin <= 16 ? 16 : g.cin <= 32 ? 32 : ceil_div(g.cin, 64) * 64;
+    w.ci_p = conv_tc_kpad(g.cin);   // same padding rule as the fprop/dgrad operands: split planes are interchangeable between the passes
     w.chunkx = w.ci_p < 64 ? w.ci_p : 64;
     w.swx = w.chunkx * 2;
     w.nxc = w.ci_p / w.chunkx;
     if (g.kw * w.chunkx > 256) return w;
     // dy (M side)
-    w.co_p = ceil_div(g.cout, 16) * 16;
-    w.swy = (w.co_p % 64 == 0) ? 128 : (w.co_p % 32 == 0) ? 64 : 32;
+    w.co_p = conv_tc_kpad(g.cout);
+    w.swy = w.co_p >= 64 ? 128 : w.co_p * 2;
     w.chunky = w.swy / 2;
     w.mtrick = (2 * w.co_p <= 128) ? 1 : 0;
     if (w.mtrick) { w.nmc = w.co_p / w.chunky; w.mtiles = 1; }
     else {
-        // M tiles of 128 rows; pad cout to a multiple of 128 so every tile has 128 / chunky chunks
-        w.co_p = ceil_div(g.cout, 128) * 128;
+        // M tiles of 128 rows (2 chunks of 64 channels); the tensor keeps conv_tc_kpad(cout) channels, chunks past it are TMA zero fill
         w.swy = 128; w.chunky = 64;
-        w.nmc = 2; w.mtiles = w.co_p / 128;
+        w.nmc = 2; w.mtiles = ceil_div(w.co_p, 128);
     }
     w.seg = g.ow >= 128 ? 128 : g.ow;
     w.segs = ceil_div(g.ow, w.seg);
@@ -307,8 +311,9 @@ size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
     return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + wg_align(partial) + 2048;
 }
 
-int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
-                  cudaStream_t st) {
+// dy_presplit != nullptr: dy is already split (interleaved layout, conv_tc_kpad(cout) channels); then db must have been produced by the caller
+static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
+                              cudaStream_t st, const __nv_bfloat16 *dy_presplit) {
     const WgPlan w = make_wg_plan(g);
     if (!w.ok) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_wgrad_workspace_bytes(g, precision)) return MDT_EWORKSPACE;
@@ -316,17 +321,17 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
     const int T = g.kd * g.kh * g.kw;
     const long long rows_y = (long long)g.n * g.od * g.oh * g.ow, rows_x = (long long)g.n * g.d * g.h * g.w;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
-    __nv_bfloat16 *ys = reinterpret_cast<__nv_bfloat16 *>(base);
+    __nv_bfloat16 *ys = dy_presplit ? const_cast<__nv_bfloat16 *>(dy_presplit) : reinterpret_cast<__nv_bfloat16 *>(base);
     __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2));
-    auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp) {
+    auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp, int line_w) {
         long long blocks = ceil_div<long long>(rows * (Cp / 8), 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, C, Cp, planes, 0);
+        split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, rows, C, Cp, planes, line_w, nullptr, nullptr, nullptr);
         return launch_status();
     };
-    int rc = split(dy, ys, rows_y, g.cout, w.co_p);
-    if (rc) return rc;
-    if ((rc = split(x, xs, rows_x, g.cin, w.ci_p))) return rc;
+    int rc = MDT_OK;
+    if (!dy_presplit && (rc = split(dy, ys, rows_y, g.cout, w.co_p, g.ow))) return rc;
+    if ((rc = split(x, xs, rows_x, g.cin, w.ci_p, g.w))) return rc;
 
     TcWgradParams p{};
     p.NB = g.n; p.OD = g.od; p.OH = g.oh; p.OW = g.ow; p.D = g.d; p.H = g.h; p.W = g.w;
@@ -354,14 +359,14 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
 
     CUtensorMap tmY, tmX;
     {
-        const uint64_t dims[5] = {(uint64_t)w.co_p, (uint64_t)g.ow, (uint64_t)g.oh, (uint64_t)g.od, (uint64_t)g.n * planes};
-        const uint64_t str[4] = {(uint64_t)w.co_p * 2, (uint64_t)g.ow * w.co_p * 2, (uint64_t)g.oh * g.ow * w.co_p * 2,
-                                 (uint64_t)g.od * g.oh * g.ow * w.co_p * 2};
+        const uint64_t yl = (uint64_t)g.ow * w.co_p * 2;   // one W line of one plane
+        const uint64_t dims[5] = {(uint64_t)w.co_p, (uint64_t)g.ow, (uint64_t)planes, (uint64_t)g.oh, (uint64_t)g.n * g.od};
+        const uint64_t str[4] = {(uint64_t)w.co_p * 2, yl, yl * planes, yl * planes * g.oh};
         const uint32_t box[5] = {(uint32_t)w.chunky, (uint32_t)w.rows_y, 1u, 1u, 1u};
         if (!encode_bf16_tmap(&tmY, ys, 5, dims, str, box, w.swy)) return MDT_EDRIVER;
-        const uint64_t xd[5] = {(uint64_t)w.ci_p, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.d, (uint64_t)g.n * planes};
-        const uint64_t xs_[4] = {(uint64_t)w.ci_p * 2, (uint64_t)g.w * w.ci_p * 2, (uint64_t)g.h * g.w * w.ci_p * 2,
-                                 (uint64_t)g.d * g.h * g.w * w.ci_p * 2};
+        const uint64_t xl = (uint64_t)g.w * w.ci_p * 2;
+        const uint64_t xd[5] = {(uint64_t)w.ci_p, (uint64_t)g.w, (uint64_t)planes, (uint64_t)g.h, (uint64_t)g.n * g.d};
+        const uint64_t xs_[4] = {(uint64_t)w.ci_p * 2, xl, xl * planes, xl * planes * g.h};
         const uint32_t xbox[5] = {(uint32_t)w.chunkx, (uint32_t)w.rows_x, 1u, 1u, 1u};
         if (!encode_bf16_tmap(&tmX, xs, 5, xd, xs_, xbox, w.swx)) return MDT_EDRIVER;
     }
@@ -384,8 +389,53 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
         wgrad_reduce_kernel<<<(unsigned)ceil_div<long long>(total, 256), 256, 0, st>>>(p, dw);
         if ((rc = launch_status())) return rc;
     }
-    if (db) return conv_bias_grad(g, dy, db, st);
+    if (db && !dy_presplit) return conv_bias_grad(g, dy, db, st);
     return MDT_OK;
+}
+
+int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
+    return conv_tc_wgrad_impl(g, x, dy, dw, db, precision, ws, ws_bytes, st, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------ fused backward
+// One streaming pass over dy produces everything both gradient kernels need: the split planes (shared by dgrad and wgrad), the ReLU
+// mask of a fused-ReLU conv, the bias gradient, and (on request) the masked fp32 gradient for a fused residual input.
+bool conv_tc_backward_supported(const ConvGeom &g, bool need_dx) {
+    return conv_tc_wgrad_supported(g) && (!need_dx || conv_tc_supported(g, 1)) && g.cout <= 256;
+}
+
+size_t conv_tc_backward_workspace_bytes(const ConvGeom &g, bool need_dx, int precision) {
+    const int planes = precision == 1 ? 1 : 2;
+    const size_t rows_y = (size_t)g.n * g.od * g.oh * g.ow;
+    const size_t ys = wg_align(planes * rows_y * conv_tc_kpad(g.cout) * 2);
+    size_t inner = conv_tc_wgrad_workspace_bytes(g, precision);
+    if (need_dx) { const size_t d = conv_tc_workspace_bytes(g, 1, precision); if (d > inner) inner = d; }
+    return ys + inner + 4096;
+}
+
+int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const float *relu_of, const float *w, float *dx, float *dw, float *db,
+                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (!conv_tc_backward_supported(g, dx != nullptr)) return MDT_EUNSUPPORTED;
+    if (ws_bytes < conv_tc_backward_workspace_bytes(g, dx != nullptr, precision)) return MDT_EWORKSPACE;
+    const int planes = precision == 1 ? 1 : 2;
+    const int co_p = conv_tc_kpad(g.cout);
+    const long long rows_y = (long long)g.n * g.od * g.oh * g.ow;
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    __nv_bfloat16 *ys = reinterpret_cast<__nv_bfloat16 *>(base);
+    uint8_t *inner = base + wg_align((size_t)planes * rows_y * co_p * 2);
+    const size_t inner_bytes = ws_bytes - (size_t)(inner - reinterpret_cast<uint8_t *>(ws));
+    if (db) {
+        cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * g.cout, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    long long blocks = ceil_div<long long>(rows_y * (co_p / 8), 256);
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, ys, rows_y, g.cout, co_p, planes, g.ow, relu_of, dy_masked_out, db);
+    int rc = launch_status();
+    if (rc) return rc;
+    if (dx && (rc = conv_tc_run(g, 1, nullptr, w, nullptr, nullptr, dx, 0, precision, inner, inner_bytes, st, ys))) return rc;
+    return conv_tc_wgrad_impl(g, x, nullptr, dw, nullptr, precision, inner, inner_bytes, st, ys);
 }
 
 }  // namespace mdt

@@ -123,3 +123,26 @@ def test_conv2d_module_matches_torch():
     assert _rel(y, yr) < TOL
     y.sum().backward()
     assert x.grad is not None and m[0].weight.grad.shape == m[0].weight.shape
+
+
+@pytest.mark.parametrize("cin,cout,sp", [(18, 72, (8, 8, 32)), (64, 64, (4, 8, 128)), (36, 36, (8, 8, 128)), (1, 18, (8, 8, 128))])
+def test_fused_backward_relu_residual_bias(cin, cout, sp):
+    """mdt_conv3d_backward: one pass over dy feeds dgrad + wgrad, with the ReLU mask, the bias gradient and the residual gradient folded in"""
+    torch.manual_seed(cin + cout)
+    k = 1 if cout == 72 else 3
+    pad = k // 2
+    x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(cin > 1)
+    w = (torch.randn(cout, cin, k, k, k, device=DEV) / np.sqrt(cin * k ** 3)).requires_grad_(True)
+    b = torch.randn(cout, device=DEV).requires_grad_(True)
+    res = torch.randn(2, cout, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    y = C._Conv3dFn.apply(x, w, b, res, (1, 1, 1), (pad,) * 3, True, 0, 0)
+    g = torch.randn_like(y)
+    y.backward(g)
+    xd, wd, bd, rd = (t.detach().double().requires_grad_(True) for t in (x, w, b, res))
+    yr = torch.relu(F.conv3d(xd, wd, bd, padding=pad) + rd)
+    yr.backward(g.double())
+    assert _rel(w.grad, wd.grad) < TOL and _rel(b.grad, bd.grad) < TOL and _rel(res.grad, rd.grad) < TOL
+    if cin > 1:
+        assert _rel(x.grad, xd.grad) < TOL
+    d = C._desc(tuple(x.shape), tuple(w.shape), (1, 1, 1), (pad,) * 3, False, 0, 0)
+    assert L.load().mdt_conv3d_backward_fused(d, int(cin > 1)) == 1    # these shapes must take the fused path
