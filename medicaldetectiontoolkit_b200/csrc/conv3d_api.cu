@@ -2,8 +2,10 @@
 #include "conv3d_common.cuh"
 
 namespace mdt {
+// 1 = fp32 SIMT (generic implicit GEMM, or the direct stem kernels when Cin <= 4), 2 = tcgen05
 static int pick_algo(const mdt_conv3d_desc *c, const ConvGeom &g, int pass) {
     if (c->algo == 1) return 1;
+    if (c->algo == 0 && conv_stem_supported(g, pass)) return 1;   // bandwidth-bound stem: direct kernels beat a 94 %-padded MMA
     const bool tc = conv_tc_supported(g, pass);
     if (c->algo == 2) return tc ? 2 : 0;
     return tc ? 2 : 1;
@@ -37,6 +39,7 @@ int mdt_conv3d_fprop(const mdt_conv3d_desc *c, const float *x, const float *w, c
     const int algo = mdt::pick_algo(c, g, 0);
     if (algo == 0) return MDT_EUNSUPPORTED;
     if (algo == 2) return mdt::conv_tc_fprop(g, x, w, bias, residual, y, c->relu, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    if (!residual && mdt::conv_stem_supported(g, 0)) return mdt::conv_stem_fprop(g, x, w, bias, y, c->relu, mdt::as_stream(stream));
     return mdt::conv_simt_fprop(g, x, w, bias, residual, y, c->relu, ws, mdt::as_stream(stream));
 }
 
@@ -57,6 +60,7 @@ int mdt_conv3d_wgrad(const mdt_conv3d_desc *c, const float *x, const float *dy, 
     const int algo = mdt::pick_algo(c, g, 2);
     if (algo == 0) return MDT_EUNSUPPORTED;
     if (algo == 2) return mdt::conv_tc_wgrad(g, x, dy, dw, db, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    if (mdt::conv_stem_supported(g, 2)) return mdt::conv_stem_wgrad(g, x, dy, dw, db, mdt::as_stream(stream));
     return mdt::conv_simt_wgrad(g, x, dy, dw, db, mdt::as_stream(stream));
 }
 
@@ -65,6 +69,7 @@ int mdt_conv3d_backward_fused(const mdt_conv3d_desc *c, int need_dx) {
     mdt::ConvGeom g;
     if (!mdt::make_geom(c, g)) return 0;
     if (c->algo == 1) return 0;
+    if (c->algo == 0 && mdt::conv_stem_supported(g, 2)) return 0;   // stem: direct kernels
     return mdt::conv_tc_backward_supported(g, need_dx != 0) ? 1 : 0;
 }
 

@@ -29,6 +29,11 @@ int conv_simt_dgrad(const ConvGeom &g, const float *dy, const float *w, float *d
 int conv_simt_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, cudaStream_t st);
 int conv_bias_grad(const ConvGeom &g, const float *dy, float *db, cudaStream_t st);
 
+// direct stem kernels, Cin <= 4 (conv3d_stem.cu)
+bool conv_stem_supported(const ConvGeom &g, int pass);
+int conv_stem_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, float *y, int relu, cudaStream_t st);
+int conv_stem_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, cudaStream_t st);
+
 // tcgen05 (conv3d_tc.cu)
 bool conv_tc_supported(const ConvGeom &g, int pass);
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
