@@ -36,7 +36,7 @@ struct TcWgradParams {
     int mtrick;
     int swx, chunkx, nxc;            // x: swizzle bytes, channels per chunk, number of ci chunks
     int ncb_total, CB, groups, splits;
-    int planes, stages, tmem_cols;
+    int planes, stages, tmem_cols, slot_cols;
     int y_chunk_bytes, y_plane_bytes, x_plane_bytes, x_buf_bytes, stage_bytes;
     int y_tx_bytes, x_tx_bytes;      // bytes one TMA box delivers
     long long units;                 // NB * OD * OH * segs
@@ -182,7 +182,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
         const uint32_t started = *(volatile uint32_t *)&s_started;
         const int q = warp & 3;
         const int m = q * 32 + lane;
-        float *slot = p.partial + (((size_t)split * p.groups + group) * p.mtiles + mt) * (size_t)(128 * 512) + (size_t)m * 512;
+        float *slot = p.partial + (((size_t)split * p.groups + group) * p.mtiles + mt) * (size_t)(128 * p.slot_cols) + (size_t)m * p.slot_cols;
         for (int b = 0; b < ncb; ++b) {
             const bool live = (started >> b) & 1u;
             for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -223,9 +223,9 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(TcWgradParams p, floa
         const int mt = p.mtrick ? 0 : co / 128, m = p.mtrick ? co : co % 128;
         float acc = 0.f;
         for (int sp = 0; sp < p.splits; ++sp) {
-            const float *slot = p.partial + (((size_t)sp * p.groups + group) * p.mtiles + mt) * (size_t)(128 * 512) + b * ncols + col;
-            acc += slot[(size_t)m * 512];
-            if (p.mtrick && p.planes > 1) acc += slot[(size_t)(m + p.co_p) * 512];
+            const float *slot = p.partial + (((size_t)sp * p.groups + group) * p.mtiles + mt) * (size_t)(128 * p.slot_cols) + b * ncols + col;
+            acc += slot[(size_t)m * p.slot_cols];
+            if (p.mtrick && p.planes > 1) acc += slot[(size_t)(m + p.co_p) * p.slot_cols];
         }
         dw[((size_t)co * p.cin + ci) * p.T + (kd * p.KH + kh) * p.KW + kw] = acc;
     }
@@ -293,21 +293,33 @@ bool conv_tc_wgrad_supported(const ConvGeom &g) { return make_wg_plan(g).ok && t
 
 static size_t wg_align(size_t v) { return (v + 1023) / 1024 * 1024; }
 
-// split-K factor: one full wave of CTAs (1 CTA per SM: the kernel uses most of the shared memory)
+// split-K factor.  Lower bound: a full wave of CTAs.  Upper bound on the work per CTA: the tensor core's fp32 accumulation is not
+// round-to-nearest — measured on B200 (tools/wgrad_precision.py, profiles/r01_wgrad_precision.txt) the error of a TMEM accumulator grows
+// LINEARLY with the number of MMAs chained into it (~1.9e-7 of the result per MMA: 3.3e-4 after the 1771 steps a 2 x 128^3 layer gives one
+// CTA per SM).  Chains are therefore cut at kMaxChain MMAs (<= ~5e-5) and the partial sums are combined in IEEE fp32 by wgrad_reduce_kernel.
+constexpr int kMaxChain = 256;
+
 static int wg_splits(const ConvGeom &g, const WgPlan &w) {
     const long long units = (long long)g.n * g.od * g.oh * w.segs;
+    const int mmas_per_unit = w.ksteps * 2;                         // two MMAs per K step go into the same accumulator (x_hi, x_lo)
+    long long max_units = kMaxChain / mmas_per_unit;
+    if (max_units < 1) max_units = 1;
+    const long long min_splits = ceil_div<long long>(units, max_units);
     long long splits = (long long)num_sms() * w.waves / ((long long)w.groups * w.mtiles);   // w.waves CTAs per SM, co-resident
+    if (splits < min_splits) splits = min_splits;
     if (splits < 1) splits = 1;
     if (splits > units) splits = units;
     return (int)splits;
 }
+
+static int wg_slot_cols(const ConvGeom &g, const WgPlan &w) { return ceil_div(w.CB * g.kw * w.chunkx, 16) * 16; }
 
 size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
     const WgPlan w = make_wg_plan(g);
     if (!w.ok) return 0;
     const int planes = precision == 1 ? 1 : 2;
     const size_t rows_y = (size_t)g.n * g.od * g.oh * g.ow, rows_x = (size_t)g.n * g.d * g.h * g.w;
-    const size_t partial = (size_t)wg_splits(g, w) * w.groups * w.mtiles * 128 * 512 * sizeof(float);
+    const size_t partial = (size_t)wg_splits(g, w) * w.groups * w.mtiles * 128 * wg_slot_cols(g, w) * sizeof(float);
     return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + wg_align(partial) + 2048;
 }
 
@@ -355,6 +367,7 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     p.units = (long long)g.n * g.od * g.oh * w.segs;
     p.splits = wg_splits(g, w);
     p.mtiles = w.mtiles;
+    p.slot_cols = wg_slot_cols(g, w);
     p.partial = reinterpret_cast<float *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2) + wg_align((size_t)planes * rows_x * w.ci_p * 2));
 
     CUtensorMap tmY, tmX;
