@@ -296,8 +296,8 @@ static size_t wg_align(size_t v) { return (v + 1023) / 1024 * 1024; }
 // split-K factor.  Lower bound: a full wave of CTAs.  Upper bound on the work per CTA: the tensor core's fp32 accumulation is not
 // round-to-nearest — measured on B200 (tools/wgrad_precision.py, profiles/r01_wgrad_precision.txt) the error of a TMEM accumulator grows
 // LINEARLY with the number of MMAs chained into it (~1.9e-7 of the result per MMA: 3.3e-4 after the 1771 steps a 2 x 128^3 layer gives one
-// CTA per SM).  Chains are therefore cut at kMaxChain MMAs (<= ~5e-5) and the partial sums are combined in IEEE fp32 by wgrad_reduce_kernel.
-constexpr int kMaxChain = 256;
+// CTA per SM).  Chains are therefore cut at kMaxChain MMAs (measured <= 1e-5 at every size) and the partial sums are combined in IEEE fp32 by wgrad_reduce_kernel.
+constexpr int kMaxChain = 512;
 
 static int wg_splits(const ConvGeom &g, const WgPlan &w) {
     const long long units = (long long)g.n * g.od * g.oh * w.segs;

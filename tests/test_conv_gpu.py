@@ -141,8 +141,11 @@ def test_fused_backward_relu_residual_bias(cin, cout, sp):
     g = torch.randn_like(y)
     y.backward(g)
     xd, wd, bd, rd = (t.detach().double().requires_grad_(True) for t in (x, w, b, res))
-    yr = torch.relu(F.conv3d(xd, wd, bd, padding=pad) + rd)
-    yr.backward(g.double())
+    pre = F.conv3d(xd, wd, bd, padding=pad) + rd
+    assert _rel(y, torch.relu(pre)) < TOL
+    # the reference backward uses OUR forward's ReLU mask: a pre-activation within rounding distance of zero may legitimately fall on either
+    # side, and one flipped element would dominate a max-norm comparison of the gradients (see tests/test_model_gpu.py::_rel_l2)
+    pre.backward(g.double() * (y.detach() > 0))
     assert _rel(w.grad, wd.grad) < TOL and _rel(b.grad, bd.grad) < TOL and _rel(res.grad, rd.grad) < TOL
     if cin > 1:
         assert _rel(x.grad, xd.grad) < TOL
