@@ -526,7 +526,16 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     p.b_chunk_bytes = (int)align_up((size_t)p.TPS * planes * p.b_plane_bytes, 1024);
     p.a_region_bytes = p.CPS * p.a_chunk_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
-    p.Q = 1;   // accumulator chains: measured to make no difference (the accumulate dependency is not the limiter); 1 keeps TMEM small
+    // Accumulator chains.  For speed one chain is enough (the accumulate dependency is not the limiter), but the tensor core's fp32 accumulation
+    // truncates: the error of a TMEM accumulator grows ~1e-7 of the result per chained MMA (tools/wgrad_precision.py).  3x3x3 layers chain
+    // <= 216 MMAs (2e-5); the 7x7x7 stem conv would chain 1372, so its MMAs rotate over Q accumulators that the epilogue adds in IEEE fp32.
+    {
+        const int chain = g.kd * g.kh * g.kw * pl.nchunks * (pl.swz / 32) * (planes > 1 ? 2 : 1);
+        p.Q = (chain + 511) / 512;
+        const int acc1 = (planes > 1 ? 2 : 1) * pl.NT;
+        while (p.Q > 1 && p.Q * acc1 > 256) --p.Q;
+        if (p.Q < 1) p.Q = 1;
+    }
     if (const char *e = getenv("MDT_TC_Q")) { const int v = atoi(e); if (v >= 1 && v <= p.Q) p.Q = v; }
     p.wreps = weight_reps(pl, T, planes);
 
