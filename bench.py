@@ -212,6 +212,18 @@ def main():
         torch.cuda.synchronize()
         conv_ms = sum(a.elapsed_time(b) for a, b, _ in C.EVENT_LOG) / args.steps
         n_conv_calls = len(C.EVENT_LOG) / args.steps
+        # the single heaviest launch: forward conv of the largest-FLOP layer (P0_conv2 36->36 k3 at full resolution for the 128^3 config)
+        per_tag = {}
+        for a, b, tag in C.EVENT_LOG:
+            if tag is not None and tag[0] == 0:
+                per_tag.setdefault(tag, []).append(a.elapsed_time(b))
+        dom = None
+        for tag, ts in per_tag.items():
+            _, xs, ws, st, which = tag
+            fl = 2.0 * xs[0] * (xs[2] // st[0]) * (xs[3] // st[1]) * (xs[4] // st[2]) * ws[0] * ws[1] * ws[2] * ws[3] * ws[4]
+            calls_per_step = len(ts) / args.steps
+            if dom is None or fl > dom[0]:
+                dom = (fl, sum(ts) / len(ts), tag, calls_per_step)
     C.EVENT_LOG = None
     # --- end to end through the public API with host buffers
     ms_e2e = timed(host_batches, args.steps)
@@ -240,6 +252,13 @@ def main():
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)",
                 "algorithmic_flops_per_step": step_flops, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms_dev / args.steps)}
+        if dom is not None:
+            fl, ms_k, tag, _ = dom
+            roof["dominant_launch"] = {
+                "kernel": "conv_tc_kernel fprop %d->%d k%s on %s (incl. its operand split/pack launches)" % (tag[1][1], tag[2][0], "x".join(map(str, tag[2][2:])), "x".join(map(str, tag[1]))),
+                "algorithmic_flops": fl, "ms": ms_k, "achieved": fl / ms_k / 1e9, "unit": "TFLOP/s", "frac": fl / ms_k / 1e9 / peak_tf,
+                "traffic": 1.655e9 if tuple(tag[1]) == (2, 36, 128, 128, 128) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/r01_ncu_conv_tc_fprop_p0_36.txt): 1.074 GB + 0.581 GB; algorithmic minimum 4*(in+out) = 1.21 GB"}
     h2d = sum(int(hb['data'].numel() * hb['data'].element_size() + hb['seg'].numel() * hb['seg'].element_size()) for hb in host_batches[:1])
     d2h = int(args.batch * np.prod(patch)) + 60 * 9 * 4 + 5 * 4  # seg_preds uint8 + detections + loss scalars
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -533,7 +533,7 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
         const int chain = g.kd * g.kh * g.kw * pl.nchunks * (pl.swz / 32) * (planes > 1 ? 2 : 1);
         p.Q = (chain + 511) / 512;
         const int acc1 = (planes > 1 ? 2 : 1) * pl.NT;
-        while (p.Q > 1 && p.Q * acc1 > 256) --p.Q;
+        while (p.Q > 1 && p.Q * acc1 > 128) --p.Q;   // keep the TMEM footprint at <= 128 columns (4 CTAs per SM)
         if (p.Q < 1) p.Q = 1;
     }
     if (const char *e = getenv("MDT_TC_Q")) { const int v = atoi(e); if (v >= 1 && v <= p.Q) p.Q = v; }
