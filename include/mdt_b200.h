@@ -126,11 +126,20 @@ int mdt_conv3d_wgrad(const mdt_conv3d_desc *desc_host, const float *x, const flo
 /* Fused backward of one conv layer (tcgen05 path): ONE streaming pass over dy yields the split-bf16 operand shared by dgrad and wgrad, applies
  * the ReLU mask of a fused-ReLU conv (y_relu = its forward output, NULL = no mask; replaces aten::threshold_backward of the reference graph),
  * accumulates db, and optionally writes the masked fp32 gradient (dy_masked_out, needed as the gradient of a fused residual input).
- * dx may be NULL (first layer).  mdt_conv3d_backward_fused() tells whether this path applies; otherwise use dgrad + wgrad. */
+ * dx may be NULL (first layer).  mdt_conv3d_backward_fused() tells whether this path applies; otherwise use dgrad + wgrad.
 int mdt_conv3d_backward_fused(const mdt_conv3d_desc *desc_host, int need_dx);
 size_t mdt_conv3d_backward_workspace_bytes(const mdt_conv3d_desc *desc_host, int need_dx);
-int mdt_conv3d_backward(const mdt_conv3d_desc *desc_host, const float *x, const float *dy, const float *y_relu, const float *w, float *dx,
-                        float *dw, float *db, float *dy_masked_out, void *workspace, size_t workspace_bytes, void *stream);
+ * x_split (optional, else NULL and x is split internally): the canonical split form of x produced by mdt_conv3d_split. */
+int mdt_conv3d_backward(const mdt_conv3d_desc *desc_host, const float *x, const void *x_split, const float *dy, const float *y_relu,
+                        const float *w, float *dx, float *dw, float *db, float *dy_masked_out, void *workspace, size_t workspace_bytes,
+                        void *stream);
+/* Canonical split form of an activation tensor (two bf16 planes, channels padded, W-line interleaved): it depends on the tensor alone, so ONE
+ * split serves every conv that reads the tensor (sibling layers, fprop and the later weight gradient).  mdt_conv3d_split_bytes gives the buffer
+ * size for the INPUT x of `desc`; mdt_conv3d_fprop_presplit is mdt_conv3d_fprop on such a buffer (tcgen05 path only, else MDT_EUNSUPPORTED). */
+size_t mdt_conv3d_split_bytes(const mdt_conv3d_desc *desc_host);
+int mdt_conv3d_split(const mdt_conv3d_desc *desc_host, const float *x, void *x_split, void *stream);
+int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *desc_host, const void *x_split, const float *w, const float *bias, const float *residual,
+                              float *y, void *workspace, size_t workspace_bytes, void *stream);
 /* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
 /* ------------------------------------------------------------- decoder up-sampling -----------------------------------------------------------

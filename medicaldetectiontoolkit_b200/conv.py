@@ -88,8 +88,24 @@ def _out_shape(x_shape, w_shape, stride, padding):
             (w + 2 * padding[2] - kw) // stride[2] + 1)
 
 
-def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, precision=None, algo=None):
-    """y = relu?(conv3d(x, weight) + bias (+ residual)); x logical [N, C, D, H, W]; returns a channels_last_3d tensor. No autograd."""
+def _split_of(lib, x, d, precision):
+    """canonical split form of x (mdt_conv3d_split), cached ON the tensor: sibling convs reading the same activation and the later weight
+    gradient reuse it instead of re-splitting (the form depends on the tensor alone: channel count and W)"""
+    hit = getattr(x, "_mdt_split", None)
+    if hit is not None and hit[1] == x._version and hit[2] == precision:
+        return hit[0]
+    xs = torch.empty(lib.mdt_conv3d_split_bytes(d), dtype=torch.uint8, device=x.device)
+    L.check(lib.mdt_conv3d_split(d, L.ptr(x), L.ptr(xs), L.stream_ptr()))
+    try:
+        x._mdt_split = (xs, x._version, precision)
+    except Exception:
+        pass
+    return xs
+
+
+def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, precision=None, algo=None, want_split=False):
+    """y = relu?(conv3d(x, weight) + bias (+ residual)); x logical [N, C, D, H, W]; returns a channels_last_3d tensor. No autograd.
+    want_split: also return the split form of x used by the tcgen05 path (or None) so the caller can hand it to the backward pass."""
     lib = L.load()
     L.require_cuda(x, weight, bias, residual)
     precision = DEFAULT_PRECISION if precision is None else precision
@@ -103,9 +119,14 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
     nbytes, which = _plan(lib, d, 0)
     ws = _workspace(nbytes, x.device)
     ev = _ev_start()
-    L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    xs = None
+    if which == 2:
+        xs = _split_of(lib, x, d, precision)
+        L.check(lib.mdt_conv3d_fprop_presplit(d, L.ptr(xs), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    else:
+        L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
     _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), which))
-    return y
+    return (y, xs) if want_split else y
 
 
 def conv3d_dgrad(dy, weight, x_shape, stride, padding, precision=None, algo=None):
@@ -144,7 +165,7 @@ def conv3d_wgrad(x, dy, w_shape, stride, padding, want_bias, precision=None, alg
 _bwd_plan_cache = {}
 
 
-def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, want_masked, precision=None, algo=None):
+def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, want_masked, precision=None, algo=None, x_split=None):
     """Fused backward of one conv (see mdt_conv3d_backward in include/mdt_b200.h).  Returns (dx|None, dw, db|None, gy_masked|None), or None when
     the fused tcgen05 path does not apply to this shape (caller then runs mask + dgrad + wgrad separately)."""
     lib = L.load()
@@ -168,8 +189,8 @@ def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, 
     gm = torch.empty_like(gy) if want_masked else None
     ws = _workspace(plan[1], dev)
     ev = _ev_start()
-    L.check(lib.mdt_conv3d_backward(d, L.ptr(x), L.ptr(gy), L.ptr(y_relu), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(gm), L.ptr(ws),
-                                    ws.numel(), L.stream_ptr()))
+    L.check(lib.mdt_conv3d_backward(d, L.ptr(x), L.ptr(x_split), L.ptr(gy), L.ptr(y_relu), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(gm),
+                                    L.ptr(ws), ws.numel(), L.stream_ptr()))
     _ev_end(ev, (3, tuple(x.shape), tuple(w.shape), tuple(stride), 2))
     return dx, dw, db, gm
 
@@ -177,8 +198,10 @@ def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, 
 class _Conv3dFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, stride, padding, relu, precision, algo):
-        y = conv3d_forward(x, weight, bias, stride, padding, relu, residual, precision, algo)
-        ctx.cfg = (stride, padding, relu, precision, algo, tuple(x.shape), bias is not None, residual is not None)
+        prec = DEFAULT_PRECISION if precision is None else precision
+        y, xs = conv3d_forward(x, weight, bias, stride, padding, relu, residual, prec, algo, want_split=True)
+        ctx.cfg = (stride, padding, relu, prec, algo, tuple(x.shape), bias is not None, residual is not None)
+        ctx.xs = xs   # split form of x: the weight gradient reads it instead of splitting x again
         ctx.save_for_backward(x, weight, y if relu else None)
         return y
 
@@ -190,7 +213,8 @@ class _Conv3dFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2])
         if need_w:
             want_masked = has_res and ctx.needs_input_grad[3] and relu
-            fused = conv3d_backward(x, gy, y if relu else None, weight, stride, padding, ctx.needs_input_grad[0], has_bias, want_masked, precision, algo)
+            fused = conv3d_backward(x, gy, y if relu else None, weight, stride, padding, ctx.needs_input_grad[0], has_bias, want_masked, precision, algo,
+                                    x_split=getattr(ctx, 'xs', None))
             if fused is not None:
                 gx, gw, gb, gm = fused
                 gres = (gm if relu else gy) if (has_res and ctx.needs_input_grad[3]) else None

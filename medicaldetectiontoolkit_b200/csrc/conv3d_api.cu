@@ -79,13 +79,34 @@ size_t mdt_conv3d_backward_workspace_bytes(const mdt_conv3d_desc *c, int need_dx
     return mdt::conv_tc_backward_workspace_bytes(g, need_dx != 0, c->precision) + 256;
 }
 
-int mdt_conv3d_backward(const mdt_conv3d_desc *c, const float *x, const float *dy, const float *y_relu, const float *w, float *dx, float *dw,
-                        float *db, float *dy_masked_out, void *ws, size_t ws_bytes, void *stream) {
+size_t mdt_conv3d_split_bytes(const mdt_conv3d_desc *c) {
     mdt::ConvGeom g;
-    if (!mdt::make_geom(c, g) || !x || !dy || !w || !dw) return MDT_EINVAL;
+    if (!mdt::make_geom(c, g)) return 0;
+    return mdt::conv_tc_split_bytes((long long)g.n * g.d * g.h * g.w, g.cin, c->precision);
+}
+
+int mdt_conv3d_split(const mdt_conv3d_desc *c, const float *x, void *x_split, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x || !x_split) return MDT_EINVAL;
+    return mdt::conv_tc_split(x, (long long)g.n * g.d * g.h * g.w, g.cin, g.w, c->precision, x_split, mdt::as_stream(stream));
+}
+
+int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *c, const void *x_split, const float *w, const float *bias, const float *residual, float *y,
+                              void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x_split || !w || !y) return MDT_EINVAL;
+    if (mdt::pick_algo(c, g, 0) != 2) return MDT_EUNSUPPORTED;
+    if (ws_bytes < mdt_conv3d_workspace_bytes(c, 0) || !ws) return MDT_EWORKSPACE;
+    return mdt::conv_tc_fprop_presplit(g, x_split, w, bias, residual, y, c->relu, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+}
+
+int mdt_conv3d_backward(const mdt_conv3d_desc *c, const float *x, const void *x_split, const float *dy, const float *y_relu, const float *w,
+                        float *dx, float *dw, float *db, float *dy_masked_out, void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || (!x && !x_split) || !dy || !w || !dw) return MDT_EINVAL;
     if (!mdt_conv3d_backward_fused(c, dx != nullptr)) return MDT_EUNSUPPORTED;
     if (!ws || ws_bytes < mdt_conv3d_backward_workspace_bytes(c, dx != nullptr)) return MDT_EWORKSPACE;
-    return mdt::conv_tc_backward(g, x, dy, y_relu, w, dx, dw, db, dy_masked_out, c->precision, ws, ws_bytes, mdt::as_stream(stream));
+    return mdt::conv_tc_backward(g, x, dy, y_relu, w, dx, dw, db, dy_masked_out, c->precision, ws, ws_bytes, mdt::as_stream(stream), x_split);
 }
 
 }  // extern "C"

@@ -47,6 +47,10 @@ int conv_tc_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw,
 bool conv_tc_backward_supported(const ConvGeom &g, bool need_dx);
 size_t conv_tc_backward_workspace_bytes(const ConvGeom &g, bool need_dx, int precision);
 int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const float *relu_of, const float *w, float *dx, float *dw, float *db,
-                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st);
+                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const void *x_split);
+size_t conv_tc_split_bytes(long long rows, int channels, int precision);
+int conv_tc_split(const float *x, long long rows, int channels, int line_w, int precision, void *out, cudaStream_t st);
+int conv_tc_fprop_presplit(const ConvGeom &g, const void *x_split, const float *w, const float *bias, const float *residual, float *y, int relu,
+                           int precision, void *ws, size_t ws_bytes, cudaStream_t st);
 
 }  // namespace mdt

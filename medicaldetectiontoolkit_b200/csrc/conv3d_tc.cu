@@ -42,6 +42,10 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
     const int groups = Cp / 8;  // 8 channels (16 bytes of bf16) per thread
     const long long total = rows * groups;
     const long long plane_stride = inter_w > 0 ? (long long)inter_w * Cp : rows * Cp;
+    // when the grid stride is a multiple of `groups`, a thread keeps the same 8 channels for all its rows: column sums then live in
+    // registers and touch shared memory once per thread instead of once per element
+    const bool reg_sum = colsum && ((long long)gridDim.x * blockDim.x) % groups == 0;
+    float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (colsum) {
         for (int i = threadIdx.x; i < Cp && i < 256; i += blockDim.x) s_sum[i] = 0.f;
         __syncthreads();
@@ -61,7 +65,10 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
             for (int k = 0; k < 8; ++k)
                 if (c0 + k < C) masked_out[r * C + c0 + k] = v[k];
         }
-        if (colsum) {
+        if (reg_sum) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) rs[k] += v[k];
+        } else if (colsum) {
 #pragma unroll
             for (int k = 0; k < 8; ++k)
                 if (c0 + k < C && v[k] != 0.f) atomicAdd(&s_sum[c0 + k], v[k]);
@@ -77,6 +84,12 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
         else off = r * Cp + c0;
         *reinterpret_cast<uint4 *>(dst + off) = *reinterpret_cast<const uint4 *>(hi);
         if (planes > 1) *reinterpret_cast<uint4 *>(dst + off + plane_stride) = *reinterpret_cast<const uint4 *>(lo);
+    }
+    if (reg_sum) {
+        const int c0 = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % groups) * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (c0 + k < C && rs[k] != 0.f) atomicAdd(&s_sum[c0 + k], rs[k]);
     }
     if (colsum) {
         __syncthreads();
@@ -566,6 +579,10 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
 int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
                   void *ws, size_t ws_bytes, cudaStream_t st) {
     return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st, nullptr);
+}
+int conv_tc_fprop_presplit(const ConvGeom &g, const void *x_split, const float *w, const float *bias, const float *residual, float *y, int relu,
+                           int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+    return conv_tc_run(g, 0, nullptr, w, bias, residual, y, relu, precision, ws, ws_bytes, st, reinterpret_cast<const __nv_bfloat16 *>(x_split));
 }
 int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
     return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st, nullptr);

@@ -325,7 +325,7 @@ size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
 
 // dy_presplit != nullptr: dy is already split (interleaved layout, conv_tc_kpad(cout) channels); then db must have been produced by the caller
 static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, int precision, void *ws, size_t ws_bytes,
-                              cudaStream_t st, const __nv_bfloat16 *dy_presplit) {
+                              cudaStream_t st, const __nv_bfloat16 *dy_presplit, const __nv_bfloat16 *x_presplit = nullptr) {
     const WgPlan w = make_wg_plan(g);
     if (!w.ok) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_wgrad_workspace_bytes(g, precision)) return MDT_EWORKSPACE;
@@ -334,7 +334,8 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     const long long rows_y = (long long)g.n * g.od * g.oh * g.ow, rows_x = (long long)g.n * g.d * g.h * g.w;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     __nv_bfloat16 *ys = dy_presplit ? const_cast<__nv_bfloat16 *>(dy_presplit) : reinterpret_cast<__nv_bfloat16 *>(base);
-    __nv_bfloat16 *xs = reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2));
+    __nv_bfloat16 *xs = x_presplit ? const_cast<__nv_bfloat16 *>(x_presplit)
+                                   : reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2));
     auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp, int line_w) {
         long long blocks = ceil_div<long long>(rows * (Cp / 8), 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
@@ -343,7 +344,7 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     };
     int rc = MDT_OK;
     if (!dy_presplit && (rc = split(dy, ys, rows_y, g.cout, w.co_p, g.ow))) return rc;
-    if ((rc = split(x, xs, rows_x, g.cin, w.ci_p, g.w))) return rc;
+    if (!x_presplit && (rc = split(x, xs, rows_x, g.cin, w.ci_p, g.w))) return rc;
 
     TcWgradParams p{};
     p.NB = g.n; p.OD = g.od; p.OH = g.oh; p.OW = g.ow; p.D = g.d; p.H = g.h; p.W = g.w;
@@ -428,7 +429,7 @@ size_t conv_tc_backward_workspace_bytes(const ConvGeom &g, bool need_dx, int pre
 }
 
 int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const float *relu_of, const float *w, float *dx, float *dw, float *db,
-                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
+                     float *dy_masked_out, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const void *x_split) {
     if (!conv_tc_backward_supported(g, dx != nullptr)) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_backward_workspace_bytes(g, dx != nullptr, precision)) return MDT_EWORKSPACE;
     const int planes = precision == 1 ? 1 : 2;
@@ -448,7 +449,21 @@ int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const f
     int rc = launch_status();
     if (rc) return rc;
     if (dx && (rc = conv_tc_run(g, 1, nullptr, w, nullptr, nullptr, dx, 0, precision, inner, inner_bytes, st, ys))) return rc;
-    return conv_tc_wgrad_impl(g, x, nullptr, dw, nullptr, precision, inner, inner_bytes, st, ys);
+    return conv_tc_wgrad_impl(g, x, nullptr, dw, nullptr, precision, inner, inner_bytes, st, ys, reinterpret_cast<const __nv_bfloat16 *>(x_split));
+}
+
+// ---- canonical split form of an activation tensor [N, D, H, W, C]: it depends on the tensor alone (C -> conv_tc_kpad(C), W), so one split can
+// serve every consumer (sibling convs in the forward pass, the weight gradient in the backward pass)
+size_t conv_tc_split_bytes(long long rows, int channels, int precision) {
+    return wg_align((size_t)(precision == 1 ? 1 : 2) * rows * conv_tc_kpad(channels) * 2);
+}
+
+int conv_tc_split(const float *x, long long rows, int channels, int line_w, int precision, void *out, cudaStream_t st) {
+    const int planes = precision == 1 ? 1 : 2, cp = conv_tc_kpad(channels);
+    long long blocks = ceil_div<long long>(rows * (cp / 8), 256);
+    if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
+    split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16 *>(out), rows, channels, cp, planes, line_w, nullptr, nullptr, nullptr);
+    return launch_status();
 }
 
 }  // namespace mdt
