@@ -127,9 +127,9 @@ int mdt_conv3d_wgrad(const mdt_conv3d_desc *desc_host, const float *x, const flo
  * the ReLU mask of a fused-ReLU conv (y_relu = its forward output, NULL = no mask; replaces aten::threshold_backward of the reference graph),
  * accumulates db, and optionally writes the masked fp32 gradient (dy_masked_out, needed as the gradient of a fused residual input).
  * dx may be NULL (first layer).  mdt_conv3d_backward_fused() tells whether this path applies; otherwise use dgrad + wgrad.
+ * x_split (optional, else NULL and x is split internally): the canonical split form of x produced by mdt_conv3d_split. */
 int mdt_conv3d_backward_fused(const mdt_conv3d_desc *desc_host, int need_dx);
 size_t mdt_conv3d_backward_workspace_bytes(const mdt_conv3d_desc *desc_host, int need_dx);
- * x_split (optional, else NULL and x is split internally): the canonical split form of x produced by mdt_conv3d_split. */
 int mdt_conv3d_backward(const mdt_conv3d_desc *desc_host, const float *x, const void *x_split, const float *dy, const float *y_relu,
                         const float *w, float *dx, float *dw, float *db, float *dy_masked_out, void *workspace, size_t workspace_bytes,
                         void *stream);
