@@ -149,7 +149,21 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
             s_count = cnt;
         }
         __syncthreads();
-        if ((s_kept >> r) & 1ULL) {
+        const unsigned long long kept_now = s_kept;
+        if (__popcll(kept_now) <= 8) {
+            // few survivors in this block (the usual case once most boxes are suppressed): all 1024 threads stream each kept row, one word each
+            unsigned long long k = kept_now;
+            while (k) {
+                const int i = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                const unsigned long long *row = mask + (size_t)(base + i) * col_blocks;
+                for (int j = b + 1 + threadIdx.x; j < col_blocks; j += kScanThreads) {
+                    const unsigned long long v = row[j];
+                    if (v) atomicOr(&remv[j], v);
+                }
+            }
+        } else if ((kept_now >> r) & 1ULL) {
+            // many survivors: 64 rows in parallel, 16 word-lanes each
             const unsigned long long *row = mask + (size_t)(base + r) * col_blocks;
 #pragma unroll 4
             for (int j = b + 1 + l; j < col_blocks; j += kScanLanes) {
