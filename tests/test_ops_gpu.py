@@ -52,7 +52,7 @@ def test_nms_rpn_and_retina_shapes_vs_oracle():
     """cfg3 RPN shape (6000 unrounded boxes, 0.7) and a Retina-style set (rounded, 1e-5)"""
     b = O.synth_boxes(6000, 3, seed=5, rounded=False)
     assert _keep(b, 0.7, 3).tolist() == O.nms(b, 0.7, 3).tolist()
-    b = O.synth_boxes(20000, 3, seed=6, rounded=True)
+    b = O.synth_boxes(8000, 3, seed=6, rounded=True)   # CPU oracle is O(N^2): keep it to ~1 s even on a loaded host
     assert _keep(b, 1e-5, 3).tolist() == O.nms(b, 1e-5, 3).tolist()
     b = O.synth_boxes(6000, 2, seed=7, rounded=False)
     assert _keep(b, 0.7, 2).tolist() == O.nms(b, 0.7, 2).tolist()
@@ -201,9 +201,9 @@ def test_matching_cfg4_and_full_grid_vs_oracle():
     rs = np.random.RandomState(0)
     sub = full[rs.permutation(full.shape[0])[:50000]]
     from golden_cfg import rand_gt
-    for anchors, G in [(sub, 8), (sub, 64), (full, 8), (sub, 600)]:
+    for anchors, G in [(sub, 8), (sub, 64), (full, 8), (sub[:8000], 600)]:   # the numpy oracle materialises A x G fp64
         gt = rand_gt(rs, G, (128, 128, 128), 3, 4, 48).astype(np.float64)
-        gt[0] = anchors[12345 % anchors.shape[0]]          # exact IoU 1.0 hit
+        gt[0] = anchors[2345 % anchors.shape[0]]           # exact IoU 1.0 hit
         if G >= 8:
             gt[5] = gt[2]                                   # duplicate GT: tie in the row argmax, later GT wins the column step
         cls = rs.randint(1, 3, size=G).astype(np.int32)
