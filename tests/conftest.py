@@ -11,6 +11,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The GPU boxes are shared hosts: torch's default of one CPU thread per visible core oversubscribes the
+    # cgroup's share and made the CPU-port parity tests (oracle/cpu_step.py) take minutes on a busy host.
+    try:
+        import torch
+        torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    except Exception:
+        pass
 
 
 @pytest.fixture(scope="session")
