@@ -44,6 +44,9 @@ __device__ __forceinline__ double iou_f64(const double *g, double vg, const doub
         inter = __dmul_rn(inter, fmax(__dsub_rn(z2, z1), 0.0));
     }
     const double uni = __dsub_rn(__dadd_rn(vg, va), inter);
+    // Disjoint boxes (almost every anchor/GT pair): 0 / uni is exactly +0.0 for uni > 0, so the ~30-instruction fp64 division is
+    // skipped. Degenerate unions (<= 0 or NaN) still take the division so that they produce numpy's -0.0 / NaN / inf bit patterns.
+    if (inter == 0.0 && uni > 0.0) return 0.0;
     return __ddiv_rn(inter, uni);
 }
 
@@ -80,8 +83,10 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restric
             const double *gb = s_gt + i * (B + 1);
             const double v = live ? iou_f64<DIM>(gb, gb[B], box, va) : -1.0;
             if (live && (g0 + i == 0 || v > best)) { best = v; best_g = g0 + i; }  // first index on ties (np.argmax axis=1)
-            // column maximum: warp max, then one atomic per warp
+            // column maximum: warp max, then one atomic per warp. Columns start at IoU 0, so a warp in which no lane overlaps this GT
+            // (the common case) has nothing to contribute and skips the shuffle tree.
             unsigned long long key = live ? ordered_key(v) : 0ULL;
+            if (!__any_sync(0xffffffffu, key > key_zero)) continue;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);

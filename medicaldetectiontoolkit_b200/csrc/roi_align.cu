@@ -57,13 +57,15 @@ __device__ __forceinline__ bool bin_taps(const RoiGeom &g, const float *__restri
 }
 
 // ---------------------------------------------------------------- generic strided scalar kernels ----------------------------------------------------------------
+// IdxT: the flat thread->element index is decomposed with five divisions; 64-bit integer division is emulated (~100 instructions each)
+// and dominated the float4 forward kernel, so launches below 2^31 elements use unsigned 32-bit indices.
 // thread -> one output scalar. c_fastest selects the thread->element order so that consecutive lanes touch consecutive addresses of the
 // dominant stream (channels for channels-last maps, z for the reference's NCDHW maps).
-template <int DIM>
+template <int DIM, typename IdxT>
 __global__ void __launch_bounds__(256) roi_fwd_scalar(RoiGeom g, const float *__restrict__ image, const float *__restrict__ boxes,
                                                      const int *__restrict__ box_ind, float *__restrict__ crops, int c_fastest, long long total) {
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        long long r = t;
+    for (IdxT t = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; t < (IdxT)total; t += (IdxT)gridDim.x * blockDim.x) {
+        IdxT r = t;
         int c, z, x, y;
         if (c_fastest) { c = r % g.C; r /= g.C; z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; }
         else           { z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; c = r % g.C; r /= g.C; }
@@ -85,11 +87,11 @@ __global__ void __launch_bounds__(256) roi_fwd_scalar(RoiGeom g, const float *__
     }
 }
 
-template <int DIM>
+template <int DIM, typename IdxT>
 __global__ void __launch_bounds__(256) roi_bwd_scalar(RoiGeom g, const float *__restrict__ grads, const float *__restrict__ boxes,
                                                      const int *__restrict__ box_ind, float *__restrict__ gimg, int c_fastest, long long total) {
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        long long r = t;
+    for (IdxT t = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; t < (IdxT)total; t += (IdxT)gridDim.x * blockDim.x) {
+        IdxT r = t;
         int c, z, x, y;
         if (c_fastest) { c = r % g.C; r /= g.C; z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; }
         else           { z = r % g.cz; r /= g.cz; x = r % g.cw; r /= g.cw; y = r % g.ch; r /= g.ch; c = r % g.C; r /= g.C; }
@@ -120,12 +122,12 @@ __global__ void __launch_bounds__(256) roi_bwd_scalar(RoiGeom g, const float *__
 
 // ---------------------------------------------------------------- channels-last float4 kernels ----------------------------------------------------------------
 // requires is[1] == 1, os[1] == 1, C % 4 == 0, all other strides % 4 == 0 and 16-byte aligned bases.
-template <int DIM>
+template <int DIM, typename IdxT>
 __global__ void __launch_bounds__(256) roi_fwd_cl4(RoiGeom g, const float *__restrict__ image, const float *__restrict__ boxes,
                                                   const int *__restrict__ box_ind, float *__restrict__ crops, long long total) {
     const int C4 = g.C >> 2;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        long long r = t;
+    for (IdxT t = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; t < (IdxT)total; t += (IdxT)gridDim.x * blockDim.x) {
+        IdxT r = t;
         const int c4 = r % C4; r /= C4;
         const int z = r % g.cz; r /= g.cz;
         const int x = r % g.cw; r /= g.cw;
@@ -156,12 +158,12 @@ __global__ void __launch_bounds__(256) roi_fwd_cl4(RoiGeom g, const float *__res
     }
 }
 
-template <int DIM>
+template <int DIM, typename IdxT>
 __global__ void __launch_bounds__(256) roi_bwd_cl4(RoiGeom g, const float *__restrict__ grads, const float *__restrict__ boxes,
                                                   const int *__restrict__ box_ind, float *__restrict__ gimg, long long total) {
     const int C4 = g.C >> 2;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        long long r = t;
+    for (IdxT t = blockIdx.x * (IdxT)blockDim.x + threadIdx.x; t < (IdxT)total; t += (IdxT)gridDim.x * blockDim.x) {
+        IdxT r = t;
         const int c4 = r % C4; r /= C4;
         const int z = r % g.cz; r /= g.cz;
         const int x = r % g.cw; r /= g.cw;
@@ -199,6 +201,9 @@ static bool cl4_ok(const RoiGeom &g, const void *img, const void *crop) {
     return ((uintptr_t)img % 16 == 0) && ((uintptr_t)crop % 16 == 0);
 }
 
+// grid-stride loops advance by gridDim*blockDim <= 148*32*256 ~ 1.2 M, so t + stride cannot wrap below 2^31 elements
+static bool fits_u32(long long total) { return total < (1LL << 31); }
+
 static int grid_for(long long total, int block) {
     long long need = (total + block - 1) / block;
     long long cap = (long long)num_sms() * 32;  // 8 resident CTAs of 256 threads per SM x 4 waves; grid-stride covers the rest
@@ -214,11 +219,14 @@ static int roi_forward(const float *image, const int64_t *is, const float *boxes
     RoiGeom g{num_boxes, batch, H, W, Z, ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = os[k]; }
     const long long total = (long long)num_boxes * C * ch * cw * cz;
+    const bool small = fits_u32(total);
     if (cl4_ok(g, image, crops)) {
-        roi_fwd_cl4<DIM><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
+        if (small) roi_fwd_cl4<DIM, unsigned><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
+        else       roi_fwd_cl4<DIM, long long><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
     } else {
         const int c_fastest = (g.is[1] == 1);
-        roi_fwd_scalar<DIM><<<grid_for(total, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, c_fastest, total);
+        if (small) roi_fwd_scalar<DIM, unsigned><<<grid_for(total, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, c_fastest, total);
+        else       roi_fwd_scalar<DIM, long long><<<grid_for(total, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, c_fastest, total);
     }
     return launch_status();
 }
@@ -237,11 +245,14 @@ static int roi_backward(const float *grads, const int64_t *gs, const float *boxe
     RoiGeom g{num_boxes, batch, H, W, Z, ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = gs[k]; }
     const long long total = (long long)num_boxes * C * ch * cw * cz;
+    const bool small = fits_u32(total);
     if (cl4_ok(g, gimg, grads)) {
-        roi_bwd_cl4<DIM><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
+        if (small) roi_bwd_cl4<DIM, unsigned><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
+        else       roi_bwd_cl4<DIM, long long><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
     } else {
         const int c_fastest = (g.is[1] == 1);
-        roi_bwd_scalar<DIM><<<grid_for(total, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, c_fastest, total);
+        if (small) roi_bwd_scalar<DIM, unsigned><<<grid_for(total, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, c_fastest, total);
+        else       roi_bwd_scalar<DIM, long long><<<grid_for(total, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, c_fastest, total);
     }
     return launch_status();
 }

@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+# Evidence trip (under gpurun, repo root): tests, microbench, ncu launch list of one train step, one `ncu --set full` capture of every hot-path
+# kernel at its BASELINE shape (tools/ncu_ops.py), then an un-profiled bench.  Numbers printed under ncu are never bench values.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+timeout 900 python -m pytest tests -q -m gpu -x --timeout 600 --durations=12 2>&1 | tail -30 > gpurun_out/pytest_gpu.txt; cut -c1-200 gpurun_out/pytest_gpu.txt
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.txt
+timeout 400 python tools/microbench.py > gpurun_out/microbench.json 2> gpurun_out/microbench.err; tail -2 gpurun_out/microbench.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c 1100 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | cut -c1-200
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k 'regex:conv_|nms_|roi_|match_|split_rows|pack_weights|wgrad|bias_grad|stem_' -f -o gpurun_out/ops \
+    python tools/ncu_ops.py > gpurun_out/ncu_ops.log 2>&1; tail -3 gpurun_out/ncu_ops.log | cut -c1-200; ls -la gpurun_out/ops.ncu-rep
+timeout 600 python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-700 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
