@@ -11,4 +11,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k 'regex:conv_|nms_|roi_|match_|split_rows|pack_weights|wgrad|bias_grad|stem_' -f -o gpurun_out/ops \
     python tools/ncu_ops.py > gpurun_out/ncu_ops.log 2>&1; tail -3 gpurun_out/ncu_ops.log | cut -c1-200; ls -la gpurun_out/ops.ncu-rep
+ncu -i gpurun_out/ops.ncu-rep --page raw --csv > gpurun_out/ops_raw.csv 2>/dev/null; wc -c gpurun_out/ops_raw.csv
+[ "$(stat -c %s gpurun_out/ops.ncu-rep 2>/dev/null || echo 0)" -gt 45000000 ] && rm -f gpurun_out/ops.ncu-rep   # gpurun_out is capped at 64 MiB
 timeout 600 python bench.py "$@" > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-700 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
