@@ -45,7 +45,9 @@ int mdt_nms_mask_3d(int boxes_num, const float *boxes_dev, unsigned long long *m
 int mdt_nms_mask_2d(int boxes_num, const float *boxes_dev, unsigned long long *mask_dev, float nms_overlap_thresh, void *stream);
 
 /* fused: bitmask + ON-DEVICE greedy reduction (replaces the D2H copy + host loop of nms_cuda.c:33-61).
- * keep_out [N] int64: first *num_out entries are the kept row indices (into the sorted input), ascending; num_out [1] int32 (device). */
+ * keep_out [N] int64: first *num_out entries are the kept row indices (into the sorted input), ascending; num_out [1] int32 (device).
+ * workspace: the upper-triangular mask [N][ceil(N/64)] u64 followed by the reduction's suppression bitmap and control block; the
+ * reduction is a cooperative launch (<= one CTA per SM) that the call zero-initialises itself - the caller only provides the bytes. */
 size_t mdt_nms_workspace_bytes(int boxes_num);
 int mdt_nms_3d(const float *boxes_dev, int boxes_num, float nms_overlap_thresh, void *workspace, size_t workspace_bytes,
                int64_t *keep_out, int *num_out, void *stream);

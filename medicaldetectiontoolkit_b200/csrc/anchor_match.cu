@@ -50,12 +50,44 @@ __device__ __forceinline__ double iou_f64(const double *g, double vg, const doub
     return __ddiv_rn(inter, uni);
 }
 
+// A box is "regular" when every extent is > 0 and its volume is positive and finite.  For two regular boxes the intersection is
+// exactly 0 iff they are separated along some axis (min(hi) <= max(lo), decided by comparisons alone: fp64 subtraction of finite
+// numbers is 0 only for equal operands), and then numpy's IoU is 0 / (vg + va) = +0.0.  ~200 instructions of NaN-aware fp64 min/max,
+// products and a division shrink to 2*DIM comparisons for the overwhelmingly common disjoint pair (ncu: the row pass was issue-bound).
+template <int DIM>
+__device__ __forceinline__ bool box_regular(const double *b, double vol) {
+    bool ok = b[2] > b[0] && b[3] > b[1] && vol > 0.0 && vol < __longlong_as_double(0x7ff0000000000000LL);
+    if (DIM == 3) ok = ok && b[5] > b[4];
+    return ok;
+}
+template <int DIM>
+__device__ __forceinline__ bool separated(const double *g, const double *a) {
+    bool d = (g[2] <= a[0]) | (a[2] <= g[0]) | (g[3] <= a[1]) | (a[3] <= g[1]);
+    if (DIM == 3) d = d | (g[5] <= a[4]) | (a[5] <= g[4]);
+    return d;
+}
+
+// stage GT boxes [g0, g0+gn) with their volumes and regularity flags in shared memory
+template <int DIM>
+__device__ __forceinline__ void stage_gt(const double *__restrict__ gt, int g0, int gn, double *s_gt, unsigned char *s_ok) {
+    constexpr int B = 2 * DIM;
+    for (int i = threadIdx.x; i < gn; i += blockDim.x) {
+        double gb[B];
+#pragma unroll
+        for (int k = 0; k < B; ++k) { gb[k] = gt[(size_t)(g0 + i) * B + k]; s_gt[i * (B + 1) + k] = gb[k]; }
+        const double vg = box_volume<DIM>(gb);
+        s_gt[i * (B + 1) + B] = vg;
+        s_ok[i] = box_regular<DIM>(gb, vg) ? 1 : 0;
+    }
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G,
                                                         int *__restrict__ row_argmax, unsigned long long *__restrict__ col_max_key) {
     constexpr int B = 2 * DIM;
     __shared__ double s_gt[kMaxGtSmem * (B + 1)];
     __shared__ unsigned long long s_colmax[kMaxGtSmem];
+    __shared__ unsigned char s_ok[kMaxGtSmem];
     const unsigned long long key_zero = ordered_key(0.0);   // column maxima start at IoU 0 (every IoU is >= 0): zero overlaps never touch an atomic
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = a < A;
@@ -66,22 +98,19 @@ __global__ void __launch_bounds__(256) match_rows_kernel(const double *__restric
         for (int k = 0; k < B; ++k) box[k] = anchors[(size_t)a * B + k];
         va = box_volume<DIM>(box);
     }
+    const bool a_ok = live && box_regular<DIM>(box, va);
     double best = 0.0;
     int best_g = 0;
     for (int g0 = 0; g0 < G; g0 += kMaxGtSmem) {
         const int gn = min(G - g0, kMaxGtSmem);
         __syncthreads();
-        for (int i = threadIdx.x; i < gn; i += blockDim.x) {
-            double gb[B];
-#pragma unroll
-            for (int k = 0; k < B; ++k) { gb[k] = gt[(size_t)(g0 + i) * B + k]; s_gt[i * (B + 1) + k] = gb[k]; }
-            s_gt[i * (B + 1) + B] = box_volume<DIM>(gb);
-            s_colmax[i] = key_zero;
-        }
+        stage_gt<DIM>(gt, g0, gn, s_gt, s_ok);
+        for (int i = threadIdx.x; i < gn; i += blockDim.x) s_colmax[i] = key_zero;
         __syncthreads();
         for (int i = 0; i < gn; ++i) {
             const double *gb = s_gt + i * (B + 1);
-            const double v = live ? iou_f64<DIM>(gb, gb[B], box, va) : -1.0;
+            double v = live ? 0.0 : -1.0;
+            if (live && !(a_ok && s_ok[i] && separated<DIM>(gb, box))) v = iou_f64<DIM>(gb, gb[B], box, va);
             if (live && (g0 + i == 0 || v > best)) { best = v; best_g = g0 + i; }  // first index on ties (np.argmax axis=1)
             // column maximum: warp max, then one atomic per warp. Columns start at IoU 0, so a warp in which no lane overlaps this GT
             // (the common case) has nothing to contribute and skips the shuffle tree.
@@ -105,20 +134,37 @@ template <int DIM>
 __global__ void __launch_bounds__(256) match_cols_kernel(const double *__restrict__ anchors, int A, const double *__restrict__ gt, int G,
                                                         const unsigned long long *__restrict__ col_max_key, int *__restrict__ col_argmax) {
     constexpr int B = 2 * DIM;
+    __shared__ double s_gt[kMaxGtSmem * (B + 1)];
+    __shared__ unsigned long long s_cm[kMaxGtSmem];
+    __shared__ unsigned char s_ok[kMaxGtSmem];
+    const unsigned long long key_zero = ordered_key(0.0);
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= A) return;
+    const bool live = a < A;
     double box[B];
+    double va = 0.0;
+    if (live) {
 #pragma unroll
-    for (int k = 0; k < B; ++k) box[k] = anchors[(size_t)a * B + k];
-    const double va = box_volume<DIM>(box);
-    for (int g = 0; g < G; ++g) {
-        double gb[B];
-#pragma unroll
-        for (int k = 0; k < B; ++k) gb[k] = __ldg(gt + (size_t)g * B + k);
-        const double v = iou_f64<DIM>(gb, box_volume<DIM>(gb), box, va);
-        // first anchor on ties (np.argmax axis=0).  A column whose maximum is 0 is won by anchor 0 by definition: resolved in finalize.
-        const unsigned long long cm = __ldg(col_max_key + g);
-        if (cm != ordered_key(0.0) && ordered_key(v) == cm) atomicMin(col_argmax + g, a);
+        for (int k = 0; k < B; ++k) box[k] = anchors[(size_t)a * B + k];
+        va = box_volume<DIM>(box);
+    }
+    const bool a_ok = live && box_regular<DIM>(box, va);
+    for (int g0 = 0; g0 < G; g0 += kMaxGtSmem) {
+        const int gn = min(G - g0, kMaxGtSmem);
+        __syncthreads();
+        stage_gt<DIM>(gt, g0, gn, s_gt, s_ok);
+        for (int i = threadIdx.x; i < gn; i += blockDim.x) s_cm[i] = col_max_key[g0 + i];
+        __syncthreads();
+        if (!live) continue;
+        for (int i = 0; i < gn; ++i) {
+            // first anchor on ties (np.argmax axis=0).  A column whose maximum is 0 is won by anchor 0 by definition: resolved in finalize,
+            // so a pair with IoU +0.0 (every separated pair) can never be a winner here.
+            const unsigned long long cm = s_cm[i];
+            if (cm == key_zero) continue;
+            const double *gb = s_gt + i * (B + 1);
+            if (a_ok && s_ok[i] && separated<DIM>(gb, box)) continue;
+            const double v = iou_f64<DIM>(gb, gb[B], box, va);
+            if (ordered_key(v) == cm) atomicMin(col_argmax + g0 + i, a);
+        }
     }
 }
 

@@ -8,6 +8,8 @@
 // Arithmetic pinning: nvcc (default -fmad=true) compiles the reference's `Sa + Sb - interS` as fma(sb_hw, sb_d, Sa) - interS
 // (checked in the sm_100a SASS of the unmodified reference file). We spell that sequence with explicit intrinsics so that neither
 // our compiler flags nor the CPU oracle (oracle/nms_oracle.c uses fmaf) can drift from it.
+#include <stdlib.h>
+
 #include "mdt_common.cuh"
 
 namespace mdt {
@@ -177,6 +179,187 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
     if (threadIdx.x == 0) *num_out = s_count;
 }
 
+// ---------------------------------------------------------------- grid-wide greedy reduction ----------------------------------------------------------------
+// The single-CTA scan above is bound by the bytes ONE SM can keep in flight: at 100 k boxes / 51 k kept it streams 380 MB of kept
+// rows at ~20 GB/s (ncu: profiles/r01_ncu_ops_summary.txt) and costs more than the mask kernel.  The grid version separates the two
+// kinds of work of the recurrence:
+//   serial phase  (CTA 0)   a CHUNK of 16 blocks = 1024 boxes is decided from shared memory only: the 1024 x 16 words of the mask that
+//                           couple the chunk's boxes with each other are staged once (128 KB), then every block costs one unrolled
+//                           64-step bit recurrence by one thread + one 1024-thread OR of the kept rows into the chunk-local words;
+//   parallel phase (all CTAs) the rows kept in the chunk are OR-ed into the global suppression bitmap for every LATER word; each
+//                           CTA owns a contiguous word range, each lane one word (register accumulator, no atomics), warps split
+//                           the kept rows, so the whole GPU's load bandwidth is used and the mask is read exactly once.
+// CTA 0 hands a ticket (keep[cnt0, cnt1) + first word) to the workers through a release/acquire sequence number and waits for all of
+// them before it reads the bitmap words of the next chunk.  Chunks in which nothing survives publish no ticket (no synchronisation).
+// Launched cooperatively (all CTAs co-resident: one per SM, 137 KB shared memory each); every spin is bounded and traps on time-out.
+constexpr int kChunkBlocks = 16;
+constexpr int kChunkRows = kChunkBlocks * kTile;   // 1024 = threads per CTA
+constexpr int kChunkPitch = kChunkBlocks + 1;      // odd word pitch: conflict-free walks down a column
+constexpr long long kSpinLimit = 6000000000LL;     // ~3 s of SM clocks
+
+struct ScanCtl {        // in the workspace behind the bitmap; zeroed before every launch
+    unsigned int seq;   // tickets published by CTA 0
+    unsigned int done;  // CTAs that completed a parallel phase, summed over tickets
+    int cnt0, cnt1;     // the ticket: keep[cnt0, cnt1) are the rows to OR in ...
+    int word0;          // ... into words [word0, col_blocks); -1 = no more tickets
+    int pad[3];
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// spin until *p >= target (monotonic counters); traps instead of hanging the GPU if the protocol is ever broken
+__device__ __forceinline__ void spin_until_ge(const unsigned int *p, unsigned int target) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(p) < target) {
+        __nanosleep(40);
+        if (clock64() - t0 > kSpinLimit) __trap();
+    }
+}
+
+// OR keep[cnt0, cnt1)'s mask rows into remv_g[word0, col_blocks): this CTA's share is a contiguous range of words
+__device__ __forceinline__ void scan_or_phase(int cnt0, int cnt1, int word0, int col_blocks, const unsigned long long *__restrict__ mask,
+                                              const int64_t *keep, unsigned long long *remv_g, unsigned long long *s_acc) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_cta = ceil_div(col_blocks - word0, (int)gridDim.x);
+    const int j0 = word0 + (int)blockIdx.x * per_cta, j1 = min(col_blocks, j0 + per_cta);
+    for (int js = j0; js < j1; js += 32) {
+        if (threadIdx.x < 32) s_acc[threadIdx.x] = 0ULL;
+        __syncthreads();
+        const int j = js + lane;
+        if (j < j1) {
+            unsigned long long acc = 0ULL;
+            int k = cnt0 + warp;
+            for (; k + 3 * 32 < cnt1; k += 4 * 32) {   // four independent rows in flight per lane
+                const int64_t r0 = __ldcg(keep + k), r1 = __ldcg(keep + k + 32), r2 = __ldcg(keep + k + 64), r3 = __ldcg(keep + k + 96);
+                const unsigned long long v0 = mask[(size_t)r0 * col_blocks + j], v1 = mask[(size_t)r1 * col_blocks + j];
+                const unsigned long long v2 = mask[(size_t)r2 * col_blocks + j], v3 = mask[(size_t)r3 * col_blocks + j];
+                acc |= (v0 | v1) | (v2 | v3);
+            }
+            for (; k < cnt1; k += 32) acc |= mask[(size_t)__ldcg(keep + k) * col_blocks + j];
+            if (acc) atomicOr(&s_acc[lane], acc);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32 && js + (int)threadIdx.x < j1 && s_acc[threadIdx.x])   // this CTA is the only writer of these words in this phase
+            remv_g[js + threadIdx.x] = __ldcg(remv_g + js + threadIdx.x) | s_acc[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kChunkRows, 1) nms_scan_grid_kernel(int n, int col_blocks, const unsigned long long *__restrict__ mask,
+                                                                     unsigned long long *remv_g, ScanCtl *ctl, int64_t *keep,
+                                                                     int *__restrict__ num_out) {
+    extern __shared__ unsigned long long s_chunk[];   // CTA 0: [kChunkRows][kChunkPitch] words of the current chunk
+    __shared__ unsigned long long s_rm[kChunkBlocks]; // suppression words of the chunk's own blocks
+    __shared__ unsigned long long s_acc[32];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_count;
+    __shared__ int s_ticket[3];
+    const int tid = threadIdx.x;
+    const unsigned int G = gridDim.x;
+
+    if (blockIdx.x != 0) {   // ---------------- workers: wait for a ticket, OR, report
+        for (unsigned int seen = 0;; ++seen) {
+            if (tid == 0) {
+                spin_until_ge(&ctl->seq, seen + 1);
+                s_ticket[0] = *(volatile int *)&ctl->cnt0; s_ticket[1] = *(volatile int *)&ctl->cnt1; s_ticket[2] = *(volatile int *)&ctl->word0;
+            }
+            __syncthreads();
+            const int cnt0 = s_ticket[0], cnt1 = s_ticket[1], word0 = s_ticket[2];
+            if (word0 < 0) return;
+            scan_or_phase(cnt0, cnt1, word0, col_blocks, mask, keep, remv_g, s_acc);
+            if (tid == 0) { __threadfence(); atomicAdd(&ctl->done, 1u); }
+            __syncthreads();   // s_ticket is rewritten next round
+        }
+    }
+
+    // ---------------- CTA 0: serial phase per chunk, then a ticket
+    if (tid == 0) s_count = 0;
+    unsigned int tickets = 0;
+    for (int c0 = 0; c0 < col_blocks; c0 += kChunkBlocks) {
+        const int nblk = min(kChunkBlocks, col_blocks - c0);
+        __syncthreads();
+        bool open = false;   // does block c0+tid still hold a box that is not suppressed?
+        if (tid < nblk) {
+            const unsigned long long w = __ldcg(remv_g + c0 + tid);   // final: every earlier ticket has been completed by every CTA
+            s_rm[tid] = w;
+            const int sz = min(n - (c0 + tid) * kTile, kTile);
+            const unsigned long long all = sz == kTile ? ~0ULL : ((1ULL << sz) - 1ULL);
+            open = (w & all) != all;
+        }
+        if (!__syncthreads_or(open)) continue;   // nothing can be kept in this chunk: no staging, no ticket
+        {   // stage the words that couple the chunk's boxes with each other (one row per thread; words left of a row's own block are
+            // never written by the mask kernel and never read below)
+            const long long row = (long long)c0 * kTile + tid;
+            if (row < n) {
+                const unsigned long long *src = mask + (size_t)row * col_blocks + c0;
+                const int own = tid / kTile;
+#pragma unroll
+                for (int w = 0; w < kChunkBlocks; ++w)
+                    if (w >= own && w < nblk) s_chunk[tid * kChunkPitch + w] = src[w];
+            }
+        }
+        __syncthreads();
+        const int cnt_begin = s_count;
+        for (int bl = 0; bl < nblk; ++bl) {
+            const int base = (c0 + bl) * kTile;
+            const int size = min(n - base, kTile);
+            if (tid == 0) {   // the reference's recurrence (nms_cuda.c:47-58) restricted to one block; loads do not depend on the chain
+                unsigned long long rm = s_rm[bl], kept = 0ULL;
+                const unsigned long long *d = s_chunk + (size_t)(bl * kTile) * kChunkPitch + bl;
+#pragma unroll 16
+                for (int i = 0; i < kTile; ++i) {
+                    const unsigned long long di = d[i * kChunkPitch];
+                    if (i < size && !((rm >> i) & 1ULL)) { kept |= 1ULL << i; rm |= di; }
+                }
+                s_kept = kept;
+            }
+            __syncthreads();
+            const unsigned long long kept = s_kept;
+            const int count = s_count;
+            if (tid < kTile && ((kept >> tid) & 1ULL)) keep[count + __popcll(kept & ((1ULL << tid) - 1ULL))] = base + tid;
+            {   // kept rows -> the later words of this chunk (64 rows x 16 words = one element per thread)
+                const int r = tid / kChunkBlocks, w = tid % kChunkBlocks;
+                if (((kept >> r) & 1ULL) && w > bl && w < nblk) {
+                    const unsigned long long v = s_chunk[(bl * kTile + r) * kChunkPitch + w];
+                    if (v) atomicOr(&s_rm[w], v);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) s_count = count + __popcll(kept);
+        }
+        __syncthreads();
+        const int cnt_end = s_count, word0 = c0 + nblk;
+        if (cnt_end > cnt_begin && word0 < col_blocks) {
+            if (G > 1) {
+                if (tid == 0) {
+                    ctl->cnt0 = cnt_begin; ctl->cnt1 = cnt_end; ctl->word0 = word0;
+                    __threadfence();   // keep[] entries (ordered by the barrier above) and the ticket before the sequence number
+                    st_release_u32(&ctl->seq, ++tickets);
+                }
+            }
+            scan_or_phase(cnt_begin, cnt_end, word0, col_blocks, mask, keep, remv_g, s_acc);
+            if (G > 1) {
+                if (tid == 0) {
+                    __threadfence();
+                    atomicAdd(&ctl->done, 1u);
+                    spin_until_ge(&ctl->done, G * tickets);   // every CTA's share of the bitmap is in L2
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *num_out = s_count;
+        if (G > 1) { ctl->word0 = -1; __threadfence(); st_release_u32(&ctl->seq, tickets + 1); }
+    }
+}
+
 template <int DIM>
 static int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, int full, cudaStream_t st) {
     if (n < 0 || (n > 0 && (!boxes || !mask))) return MDT_EINVAL;
@@ -184,6 +367,16 @@ static int launch_mask(int n, const float *boxes, unsigned long long *mask, floa
     const int cb = ceil_div(n, kTile);
     nms_mask_kernel<DIM><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
     return launch_status();
+}
+
+static size_t scan_ctl_offset(int n) {   // workspace = mask [n][cb] | remv_g [cb] | ScanCtl
+    const size_t cb = ceil_div(n, kTile);
+    return (size_t)n * cb * sizeof(unsigned long long);
+}
+
+static int scan_variant() {   // MDT_NMS_SCAN=1 selects the single-CTA scan (kept for A/B measurements); read per call, it is cheap
+    const char *e = getenv("MDT_NMS_SCAN");
+    return (e && e[0] == '1') ? 1 : 2;
 }
 
 template <int DIM>
@@ -194,18 +387,37 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
         return e == cudaSuccess ? MDT_OK : (int)e;
     }
     if (ws_bytes < mdt_nms_workspace_bytes(n)) return MDT_EWORKSPACE;
-    const int cb = ceil_div(n, kTile);
-    const size_t smem = (size_t)cb * sizeof(unsigned long long);
-    if (smem > 200 * 1024) return MDT_EUNSUPPORTED;  // N <= 1.6 M boxes
+    int cb = ceil_div(n, kTile);
     auto *mask = reinterpret_cast<unsigned long long *>(ws);
     int rc = launch_mask<DIM>(n, boxes, mask, thresh, /*full=*/0, st);
     if (rc != MDT_OK) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
+    if (scan_variant() == 1) {
+        const size_t smem = (size_t)cb * sizeof(unsigned long long);
+        if (smem > 200 * 1024) return MDT_EUNSUPPORTED;  // N <= 1.6 M boxes
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return MDT_EUNSUPPORTED;
+            attr_set = true;
+        }
+        nms_scan_kernel<<<1, kScanThreads, smem, st>>>(n, cb, mask, keep, num_out);
+        return launch_status();
     }
-    nms_scan_kernel<<<1, kScanThreads, smem, st>>>(n, cb, mask, keep, num_out);
+    auto *remv_g = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(ws) + scan_ctl_offset(n));
+    auto *ctl = reinterpret_cast<ScanCtl *>(remv_g + cb);
+    cudaError_t e = cudaMemsetAsync(remv_g, 0, (size_t)cb * sizeof(unsigned long long) + sizeof(ScanCtl), st);
+    if (e != cudaSuccess) return (int)e;
+    const size_t smem = (size_t)kChunkRows * kChunkPitch * sizeof(unsigned long long);
+    static bool grid_attr_set = false;
+    if (!grid_attr_set) {
+        if (cudaFuncSetAttribute(nms_scan_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MDT_EUNSUPPORTED;
+        grid_attr_set = true;
+    }
+    // one CTA per SM at most (cooperative launch: all co-resident); ~8 bitmap words per CTA and ticket at least
+    int grid = cb > kChunkBlocks ? ceil_div(cb - kChunkBlocks, 8) : 1;
+    if (grid > num_sms()) grid = num_sms();
+    void *args[] = {&n, &cb, &mask, &remv_g, &ctl, &keep, &num_out};
+    e = cudaLaunchCooperativeKernel((const void *)nms_scan_grid_kernel, dim3(grid), dim3(kChunkRows), args, smem, st);
+    if (e != cudaSuccess) return (int)e;
     return launch_status();
 }
 
@@ -215,8 +427,8 @@ extern "C" {
 
 size_t mdt_nms_workspace_bytes(int boxes_num) {
     if (boxes_num <= 0) return 0;
-    size_t cb = mdt::ceil_div(boxes_num, mdt::kTile);
-    return (size_t)boxes_num * cb * sizeof(unsigned long long);
+    size_t cb = mdt::ceil_div(boxes_num, mdt::kTile);   // mask [n][cb] + the grid scan's bitmap [cb] and control block
+    return (size_t)boxes_num * cb * sizeof(unsigned long long) + cb * sizeof(unsigned long long) + sizeof(mdt::ScanCtl);
 }
 
 int mdt_nms_mask_3d(int n, const float *boxes, unsigned long long *mask, float thresh, void *stream) {

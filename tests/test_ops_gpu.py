@@ -213,3 +213,35 @@ def test_matching_cfg4_and_full_grid_vs_oracle():
         assert np.array_equal(m.cpu().numpy(), want_m), G
         assert np.array_equal(arg.cpu().numpy(), want_arg), G
         assert int(npos.item()) == int((want_m > 0).sum())
+
+
+def test_matching_touching_nested_and_flat_boxes_vs_oracle():
+    """the comparison-only reject of separated pairs must reproduce numpy for touching faces, nested boxes, zero-extent (flat) GT
+    boxes and a GT that overlaps nothing (its column maximum stays 0 -> np.argmax picks anchor 0)"""
+    for dim in (2, 3):
+        B = 2 * dim
+        rs = np.random.RandomState(dim)
+        lo = rs.randint(0, 40, size=(3000, dim)).astype(np.float64)
+        ext = rs.randint(1, 24, size=(3000, dim)).astype(np.float64)
+        anchors = np.zeros((3000, B))
+        gt = np.zeros((7, B))
+        def put(dst, i, l, e):
+            dst[i, 0], dst[i, 1], dst[i, 2], dst[i, 3] = l[0], l[1], l[0] + e[0], l[1] + e[1]
+            if dim == 3:
+                dst[i, 4], dst[i, 5] = l[2], l[2] + e[2]
+        for i in range(3000):
+            put(anchors, i, lo[i], ext[i])
+        put(gt, 0, lo[10] + np.array([ext[10][0]] + [0] * (dim - 1)), ext[10])      # shares a face with anchor 10
+        put(gt, 1, lo[20] + 1, np.maximum(ext[20] - 2, 1))                            # nested in anchor 20
+        put(gt, 2, lo[30], ext[30])                                                  # identical to anchor 30
+        put(gt, 3, lo[40], ext[40] * np.array([0] + [1] * (dim - 1)))                # flat: zero extent along y
+        put(gt, 4, np.full(dim, 500.0), np.full(dim, 4.0))                           # far away from every anchor
+        put(gt, 5, lo[50] - 0.5, ext[50] + 1.0)                                      # contains anchor 50
+        put(gt, 6, lo[60] + 0.25, ext[60])                                           # shifted copy
+        cls = np.arange(1, 8).astype(np.int32)
+        m, arg, npos = MU.anchor_match_device(torch.from_numpy(anchors).to(DEV), torch.from_numpy(gt).to(DEV), torch.from_numpy(cls).to(DEV),
+                                              dim, 0.1 if dim == 2 else 0.01, 0.5)
+        want_m, want_arg = MO.match_labels(anchors, gt, cls, 0.5, dim)
+        assert np.array_equal(arg.cpu().numpy(), want_arg), dim
+        assert np.array_equal(m.cpu().numpy(), want_m), dim
+        assert int(npos.item()) == int((want_m > 0).sum())

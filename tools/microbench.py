@@ -90,6 +90,11 @@ def main():
         keep, num = NO.nms_sorted(t, thr, 3)
         rec = {"n": n, "thresh": thr, "us": us, "kept": int(num.item()), "pair_tests_per_s": n * (n - 1) / 2 / (us * 1e-6),
                "alg_bytes": 28 * n + 8 * n * ((n + 63) // 64) * 2}
+        os.environ["MDT_NMS_SCAN"] = "1"      # A/B: the single-CTA greedy reduction
+        rec["us_single_cta_scan"] = time_us(lambda: NO.nms_sorted(t, thr, 3), iters=10)
+        k1, n1 = NO.nms_sorted(t, thr, 3)
+        rec["scan_variants_agree"] = bool(int(n1.item()) == int(num.item()) and torch.equal(k1[: int(n1.item())], keep[: int(num.item())]))
+        del os.environ["MDT_NMS_SCAN"]
         if O.ref_lib("nms3d") is not None:
             times = [0.0, 0.0, 0.0]
             ref_keep = O.ref_nms(b, thr, 3, times)
