@@ -183,15 +183,17 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int n, int col_b
 // The single-CTA scan above is bound by the bytes ONE SM can keep in flight: at 100 k boxes / 51 k kept it streams 380 MB of kept
 // rows at ~20 GB/s (ncu: profiles/r01_ncu_ops_summary.txt) and costs more than the mask kernel.  The grid version separates the two
 // kinds of work of the recurrence:
-//   serial phase  (CTA 0)   a CHUNK of 16 blocks = 1024 boxes is decided from shared memory only: the 1024 x 16 words of the mask that
-//                           couple the chunk's boxes with each other are staged once (128 KB), then every block costs one unrolled
-//                           64-step bit recurrence by one thread + one 1024-thread OR of the kept rows into the chunk-local words;
-//   parallel phase (all CTAs) the rows kept in the chunk are OR-ed into the global suppression bitmap for every LATER word; each
-//                           CTA owns a contiguous word range, each lane one word (register accumulator, no atomics), warps split
-//                           the kept rows, so the whole GPU's load bandwidth is used and the mask is read exactly once.
-// CTA 0 hands a ticket (keep[cnt0, cnt1) + first word) to the workers through a release/acquire sequence number and waits for all of
-// them before it reads the bitmap words of the next chunk.  Chunks in which nothing survives publish no ticket (no synchronisation).
-// Launched cooperatively (all CTAs co-resident: one per SM, 137 KB shared memory each); every spin is bounded and traps on time-out.
+//   serial phase (CTA 0)     a CHUNK of 16 blocks = 1024 boxes is decided from shared memory only: the 1024 x 16 words of the mask that
+//                            couple the chunk's boxes with each other are staged once (rows that are still alive only), then every
+//                            block that still has a live box costs one fully unrolled 64-step bit recurrence by one thread + one
+//                            1024-thread OR of the kept rows into the chunk-local words; dead blocks cost nothing;
+//   parallel phase (workers) the rows kept in the chunk are OR-ed into the global suppression bitmap for all words from the chunk
+//                            AFTER the next one on; each worker CTA owns a contiguous word range, each lane one word (register
+//                            accumulator, no atomics), warps split the kept rows: the whole GPU's load bandwidth, mask read once.
+// CTA 0 ORs the kept rows into the NEXT chunk's 16 words itself, so it never waits for the ticket it has just published: the workers
+// run one chunk behind (software pipeline).  Tickets go through a release/acquire sequence number; chunks in which nothing survives
+// publish nothing.  Launched cooperatively (all CTAs co-resident: one per SM, 137 KB shared memory each); every spin is bounded and
+// traps on time-out instead of hanging the GPU.
 constexpr int kChunkBlocks = 16;
 constexpr int kChunkRows = kChunkBlocks * kTile;   // 1024 = threads per CTA
 constexpr int kChunkPitch = kChunkBlocks + 1;      // odd word pitch: conflict-free walks down a column
@@ -199,7 +201,7 @@ constexpr long long kSpinLimit = 6000000000LL;     // ~3 s of SM clocks
 
 struct ScanCtl {        // in the workspace behind the bitmap; zeroed before every launch
     unsigned int seq;   // tickets published by CTA 0
-    unsigned int done;  // CTAs that completed a parallel phase, summed over tickets
+    unsigned int done;  // worker CTAs that completed a ticket, summed over tickets
     int cnt0, cnt1;     // the ticket: keep[cnt0, cnt1) are the rows to OR in ...
     int word0;          // ... into words [word0, col_blocks); -1 = no more tickets
     int pad[3];
@@ -217,17 +219,18 @@ __device__ __forceinline__ void st_release_u32(unsigned int *p, unsigned int v) 
 __device__ __forceinline__ void spin_until_ge(const unsigned int *p, unsigned int target) {
     const long long t0 = clock64();
     while (ld_acquire_u32(p) < target) {
-        __nanosleep(40);
+        __nanosleep(20);
         if (clock64() - t0 > kSpinLimit) __trap();
     }
 }
 
-// OR keep[cnt0, cnt1)'s mask rows into remv_g[word0, col_blocks): this CTA's share is a contiguous range of words
-__device__ __forceinline__ void scan_or_phase(int cnt0, int cnt1, int word0, int col_blocks, const unsigned long long *__restrict__ mask,
-                                              const int64_t *keep, unsigned long long *remv_g, unsigned long long *s_acc) {
+// worker `widx` of `workers`: OR keep[cnt0, cnt1)'s mask rows into its contiguous share of remv_g[word0, col_blocks)
+__device__ __forceinline__ void scan_or_phase(int cnt0, int cnt1, int word0, int col_blocks, int widx, int workers,
+                                              const unsigned long long *__restrict__ mask, const int64_t *keep, unsigned long long *remv_g,
+                                              unsigned long long *s_acc) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per_cta = ceil_div(col_blocks - word0, (int)gridDim.x);
-    const int j0 = word0 + (int)blockIdx.x * per_cta, j1 = min(col_blocks, j0 + per_cta);
+    const int per_cta = ceil_div(col_blocks - word0, workers);
+    const int j0 = word0 + widx * per_cta, j1 = min(col_blocks, j0 + per_cta);
     for (int js = j0; js < j1; js += 32) {
         if (threadIdx.x < 32) s_acc[threadIdx.x] = 0ULL;
         __syncthreads();
@@ -245,7 +248,7 @@ __device__ __forceinline__ void scan_or_phase(int cnt0, int cnt1, int word0, int
             if (acc) atomicOr(&s_acc[lane], acc);
         }
         __syncthreads();
-        if (threadIdx.x < 32 && js + (int)threadIdx.x < j1 && s_acc[threadIdx.x])   // this CTA is the only writer of these words in this phase
+        if (threadIdx.x < 32 && js + (int)threadIdx.x < j1 && s_acc[threadIdx.x])   // this CTA is the only writer of these words for this ticket
             remv_g[js + threadIdx.x] = __ldcg(remv_g + js + threadIdx.x) | s_acc[threadIdx.x];
         __syncthreads();
     }
@@ -254,14 +257,14 @@ __device__ __forceinline__ void scan_or_phase(int cnt0, int cnt1, int word0, int
 __global__ void __launch_bounds__(kChunkRows, 1) nms_scan_grid_kernel(int n, int col_blocks, const unsigned long long *__restrict__ mask,
                                                                      unsigned long long *remv_g, ScanCtl *ctl, int64_t *keep,
                                                                      int *__restrict__ num_out) {
-    extern __shared__ unsigned long long s_chunk[];   // CTA 0: [kChunkRows][kChunkPitch] words of the current chunk
-    __shared__ unsigned long long s_rm[kChunkBlocks]; // suppression words of the chunk's own blocks
+    extern __shared__ unsigned long long s_chunk[];     // CTA 0: [kChunkRows][kChunkPitch] words of the current chunk
+    __shared__ unsigned long long s_rm[kChunkBlocks];   // suppression words of the chunk's own blocks
+    __shared__ unsigned long long s_next[kChunkBlocks]; // what this chunk's kept rows add to the NEXT chunk's words
     __shared__ unsigned long long s_acc[32];
     __shared__ unsigned long long s_kept;
-    __shared__ int s_count;
     __shared__ int s_ticket[3];
     const int tid = threadIdx.x;
-    const unsigned int G = gridDim.x;
+    const unsigned int W = gridDim.x - 1;   // worker CTAs
 
     if (blockIdx.x != 0) {   // ---------------- workers: wait for a ticket, OR, report
         for (unsigned int seen = 0;; ++seen) {
@@ -272,56 +275,67 @@ __global__ void __launch_bounds__(kChunkRows, 1) nms_scan_grid_kernel(int n, int
             __syncthreads();
             const int cnt0 = s_ticket[0], cnt1 = s_ticket[1], word0 = s_ticket[2];
             if (word0 < 0) return;
-            scan_or_phase(cnt0, cnt1, word0, col_blocks, mask, keep, remv_g, s_acc);
+            scan_or_phase(cnt0, cnt1, word0, col_blocks, (int)blockIdx.x - 1, (int)W, mask, keep, remv_g, s_acc);
             if (tid == 0) { __threadfence(); atomicAdd(&ctl->done, 1u); }
             __syncthreads();   // s_ticket is rewritten next round
         }
     }
 
-    // ---------------- CTA 0: serial phase per chunk, then a ticket
-    if (tid == 0) s_count = 0;
-    unsigned int tickets = 0;
+    // ---------------- CTA 0: serial phase per chunk; all counters below are uniform across the CTA
+    int count = 0;
+    unsigned int tickets = 0, tickets_prev = 0, tickets_prev2 = 0;   // published so far / before the previous chunk / before the one before
+    if (tid < kChunkBlocks) s_next[tid] = 0ULL;
     for (int c0 = 0; c0 < col_blocks; c0 += kChunkBlocks) {
         const int nblk = min(kChunkBlocks, col_blocks - c0);
+        tickets_prev2 = tickets_prev;
+        tickets_prev = tickets;
+        // this chunk's words are final once the tickets of all chunks up to the one before the previous are complete (a ticket starts two
+        // chunks ahead; the previous chunk's contribution is in s_next)
+        if (W > 0 && tickets_prev2 > 0 && tid == 0) spin_until_ge(&ctl->done, W * tickets_prev2);
         __syncthreads();
         bool open = false;   // does block c0+tid still hold a box that is not suppressed?
         if (tid < nblk) {
-            const unsigned long long w = __ldcg(remv_g + c0 + tid);   // final: every earlier ticket has been completed by every CTA
+            const unsigned long long w = __ldcg(remv_g + c0 + tid) | s_next[tid];
             s_rm[tid] = w;
             const int sz = min(n - (c0 + tid) * kTile, kTile);
             const unsigned long long all = sz == kTile ? ~0ULL : ((1ULL << sz) - 1ULL);
             open = (w & all) != all;
         }
-        if (!__syncthreads_or(open)) continue;   // nothing can be kept in this chunk: no staging, no ticket
-        {   // stage the words that couple the chunk's boxes with each other (one row per thread; words left of a row's own block are
-            // never written by the mask kernel and never read below)
+        const int any_open = __syncthreads_or(open);
+        if (tid < kChunkBlocks) s_next[tid] = 0ULL;
+        if (!any_open) continue;   // nothing can be kept in this chunk: no staging, no ticket
+        {   // stage the words that couple the chunk's live boxes with each other (one row per thread; words left of a row's own block are
+            // never written by the mask kernel and never read below; rows already suppressed are never read either)
             const long long row = (long long)c0 * kTile + tid;
-            if (row < n) {
+            const int own = tid / kTile;
+            if (row < n && !((s_rm[own] >> (tid % kTile)) & 1ULL)) {
                 const unsigned long long *src = mask + (size_t)row * col_blocks + c0;
-                const int own = tid / kTile;
 #pragma unroll
                 for (int w = 0; w < kChunkBlocks; ++w)
                     if (w >= own && w < nblk) s_chunk[tid * kChunkPitch + w] = src[w];
             }
         }
         __syncthreads();
-        const int cnt_begin = s_count;
+        const int cnt_begin = count;
         for (int bl = 0; bl < nblk; ++bl) {
             const int base = (c0 + bl) * kTile;
             const int size = min(n - base, kTile);
-            if (tid == 0) {   // the reference's recurrence (nms_cuda.c:47-58) restricted to one block; loads do not depend on the chain
-                unsigned long long rm = s_rm[bl], kept = 0ULL;
+            const unsigned long long all = size == kTile ? ~0ULL : ((1ULL << size) - 1ULL);
+            const unsigned long long rm0 = s_rm[bl];            // final: ordered by the barrier that ended the previous iteration
+            if ((rm0 & all) == all) continue;                   // every box of the block is suppressed already (uniform branch)
+            if (tid == 0) {   // the reference's recurrence (nms_cuda.c:47-58) restricted to one block, fully unrolled: constant bit positions,
+                              // the shared-memory loads do not depend on the chain
+                unsigned long long rm = rm0 | ~all, kept = 0ULL;
                 const unsigned long long *d = s_chunk + (size_t)(bl * kTile) * kChunkPitch + bl;
-#pragma unroll 16
+#pragma unroll
                 for (int i = 0; i < kTile; ++i) {
                     const unsigned long long di = d[i * kChunkPitch];
-                    if (i < size && !((rm >> i) & 1ULL)) { kept |= 1ULL << i; rm |= di; }
+                    if (!((rm >> i) & 1ULL)) { kept |= 1ULL << i; rm |= di; }
                 }
                 s_kept = kept;
             }
             __syncthreads();
             const unsigned long long kept = s_kept;
-            const int count = s_count;
             if (tid < kTile && ((kept >> tid) & 1ULL)) keep[count + __popcll(kept & ((1ULL << tid) - 1ULL))] = base + tid;
             {   // kept rows -> the later words of this chunk (64 rows x 16 words = one element per thread)
                 const int r = tid / kChunkBlocks, w = tid % kChunkBlocks;
@@ -330,33 +344,42 @@ __global__ void __launch_bounds__(kChunkRows, 1) nms_scan_grid_kernel(int n, int
                     if (v) atomicOr(&s_rm[w], v);
                 }
             }
+            count += __popcll(kept);
             __syncthreads();
-            if (tid == 0) s_count = count + __popcll(kept);
         }
-        __syncthreads();
-        const int cnt_end = s_count, word0 = c0 + nblk;
-        if (cnt_end > cnt_begin && word0 < col_blocks) {
-            if (G > 1) {
+        const int word0 = c0 + nblk;
+        if (count > cnt_begin && word0 < col_blocks) {
+            const int wword0 = word0 + kChunkBlocks;   // the workers start behind the next chunk
+            if (W > 0 && wword0 < col_blocks) {
                 if (tid == 0) {
-                    ctl->cnt0 = cnt_begin; ctl->cnt1 = cnt_end; ctl->word0 = word0;
-                    __threadfence();   // keep[] entries (ordered by the barrier above) and the ticket before the sequence number
-                    st_release_u32(&ctl->seq, ++tickets);
+                    if (tickets > 0) spin_until_ge(&ctl->done, W * tickets);   // the ticket slot is free again (normally long since)
+                    ctl->cnt0 = cnt_begin; ctl->cnt1 = count; ctl->word0 = wword0;
+                    __threadfence();   // keep[] entries (ordered by the barriers above) and the ticket before the sequence number
+                    st_release_u32(&ctl->seq, tickets + 1);
                 }
+                ++tickets;
+            } else if (W == 0 && wword0 < col_blocks) {   // no workers were launched (tiny grids): do their share here
+                scan_or_phase(cnt_begin, count, wword0, col_blocks, 0, 1, mask, keep, remv_g, s_acc);
             }
-            scan_or_phase(cnt_begin, cnt_end, word0, col_blocks, mask, keep, remv_g, s_acc);
-            if (G > 1) {
-                if (tid == 0) {
-                    __threadfence();
-                    atomicAdd(&ctl->done, 1u);
-                    spin_until_ge(&ctl->done, G * tickets);   // every CTA's share of the bitmap is in L2
-                }
+            // own share: the next chunk's words, 64 half-warps over the kept rows, one word per lane of a half-warp
+            const int nw = min(kChunkBlocks, col_blocks - word0);
+            const int h = tid / kChunkBlocks, l = tid % kChunkBlocks;
+            if (l < nw) {
+                unsigned long long acc = 0ULL;
+                for (int k = cnt_begin + h; k < count; k += kChunkRows / kChunkBlocks)
+                    acc |= mask[(size_t)__ldcg(keep + k) * col_blocks + word0 + l];
+                if (acc) atomicOr(&s_next[l], acc);
             }
         }
     }
-    __syncthreads();
     if (tid == 0) {
-        *num_out = s_count;
-        if (G > 1) { ctl->word0 = -1; __threadfence(); st_release_u32(&ctl->seq, tickets + 1); }
+        *num_out = count;
+        if (W > 0) {
+            if (tickets > 0) spin_until_ge(&ctl->done, W * tickets);
+            ctl->word0 = -1;
+            __threadfence();
+            st_release_u32(&ctl->seq, tickets + 1);
+        }
     }
 }
 
@@ -412,8 +435,9 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
         if (cudaFuncSetAttribute(nms_scan_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MDT_EUNSUPPORTED;
         grid_attr_set = true;
     }
-    // one CTA per SM at most (cooperative launch: all co-resident); ~8 bitmap words per CTA and ticket at least
-    int grid = cb > kChunkBlocks ? ceil_div(cb - kChunkBlocks, 8) : 1;
+    // CTA 0 + workers, one CTA per SM at most (cooperative launch: all co-resident); a ticket starts two chunks ahead of the chunk that
+    // issues it, so up to 32 blocks need no worker at all; ~8 bitmap words per worker and ticket at least
+    int grid = cb > 2 * kChunkBlocks ? 1 + ceil_div(cb - 2 * kChunkBlocks, 8) : 1;
     if (grid > num_sms()) grid = num_sms();
     void *args[] = {&n, &cb, &mask, &remv_g, &ctl, &keep, &num_out};
     e = cudaLaunchCooperativeKernel((const void *)nms_scan_grid_kernel, dim3(grid), dim3(kChunkRows), args, smem, st);

@@ -6,8 +6,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 timeout 900 python -m pytest tests -q -m gpu -x --timeout 600 --durations=12 2>&1 | tail -30 > gpurun_out/pytest_gpu.txt; cut -c1-200 gpurun_out/pytest_gpu.txt
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.txt
 timeout 400 python tools/microbench.py > gpurun_out/microbench.json 2> gpurun_out/microbench.err; tail -2 gpurun_out/microbench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2300 -c 1100 --csv --log-file gpurun_out/launches.csv \
-    python bench.py --steps 1 --warmup 2 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | cut -c1-200
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k 'regex:conv_|nms_|roi_|match_|split_rows|pack_weights|wgrad|bias_grad|stem_' -f -o gpurun_out/ops \
     python tools/ncu_ops.py > gpurun_out/ncu_ops.log 2>&1; tail -3 gpurun_out/ncu_ops.log | cut -c1-200; ls -la gpurun_out/ops.ncu-rep

@@ -45,6 +45,49 @@ def time_us(fn, iters=20, warmup=3):
     return ts[len(ts) // 2]
 
 
+def graph_us(call, reps=20):
+    """GPU-side duration of one `call` (us): `reps` calls captured into ONE CUDA graph with an L2 flush in front of each, minus the same
+    graph with the flushes only.  The event-timed numbers above include the host's launch path (~25-30 us per Python->ctypes call),
+    which hides every kernel shorter than that; this one does not."""
+    global _flush
+    if _flush is None:
+        _flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            call()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+
+        def build(with_op):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(reps):
+                    _flush.fill_(1)
+                    if with_op:
+                        call()
+            return g
+
+        def run(g):
+            ts = []
+            for _ in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3)
+            ts.sort()
+            return ts[len(ts) // 2]
+        ga, gb = build(True), build(False)
+        run(ga), run(gb)
+        return (run(ga) - run(gb)) / reps
+    except Exception as e:   # e.g. a launch type that cannot be captured
+        torch.cuda.synchronize()
+        return "graph timing failed: %s" % (str(e)[:200],)
+
+
 def main():
     out = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": PEAKS["hbm_gbs"]}
     # ---------------------------------------------------------------- RoIAlign cfg3
@@ -72,6 +115,29 @@ def main():
             us_b = time_us(lambda: torch.autograd.grad(y, xg, g, retain_graph=True))
             rec[layout] = {"fwd_us": us, "fwd_gbs": alg_fwd / us / 1e3, "fwd_frac_hbm": alg_fwd / us / 1e3 / PEAKS["hbm_gbs"],
                            "bwd_us": us_b, "bwd_gbs": alg_bwd / us_b / 1e3, "bwd_frac_hbm": alg_bwd / us_b / 1e3 / PEAKS["hbm_gbs"]}
+        # kernel-only: straight C-ABI calls on preallocated tensors inside a CUDA graph
+        from medicaldetectiontoolkit_b200 import _lib as L
+        lib = L.load()
+        xcl = torch.from_numpy(img).to(DEV).contiguous(memory_format=torch.channels_last_3d)
+        ycl = torch.empty([n, C] + list(crop), dtype=torch.float32, device=DEV, memory_format=torch.channels_last_3d)
+        gcl = torch.randn_like(ycl)
+        dxcl = torch.empty_like(xcl)
+        tbf, tii = tb.contiguous().float(), ti.contiguous().int()
+        xs, ys = L.i64arr(xcl.stride()), L.i64arr(ycl.stride())
+
+        def k_fwd():
+            L.check(lib.mdt_crop_and_resize_3d_forward(L.ptr(xcl), xs, L.ptr(tbf), L.ptr(tii), n, shape[0], shape[2], shape[3], shape[4],
+                                                       crop[0], crop[1], crop[2], C, 0.0, L.ptr(ycl), ys, L.stream_ptr()))
+
+        def k_bwd():
+            L.check(lib.mdt_crop_and_resize_3d_backward(L.ptr(gcl), ys, L.ptr(tbf), L.ptr(tii), n, shape[0], shape[2], shape[3], shape[4],
+                                                        crop[0], crop[1], crop[2], C, L.ptr(dxcl), xs, 1, dxcl.numel(), L.stream_ptr()))
+        kf, kb = graph_us(k_fwd), graph_us(k_bwd)
+        rec["channels_last_kernel_only"] = {"fwd_us": kf, "bwd_us_incl_memset": kb}
+        if not isinstance(kf, str):
+            rec["channels_last_kernel_only"].update({"fwd_gbs": alg_fwd / kf / 1e3, "fwd_frac_hbm": alg_fwd / kf / 1e3 / PEAKS["hbm_gbs"]})
+        if not isinstance(kb, str):
+            rec["channels_last_kernel_only"].update({"bwd_gbs": alg_bwd / kb / 1e3, "bwd_frac_hbm": alg_bwd / kb / 1e3 / PEAKS["hbm_gbs"]})
         if O.ref_lib("roi3d") is not None:
             t = [0.0]
             O.ref_crop_and_resize_forward(img, boxes, ind, crop, iters=20, times=t)
@@ -101,6 +167,8 @@ def main():
             rec["reference_kernel_us"] = {"mask_kernel": times[0] * 1e3, "d2h_mask": times[1] * 1e3, "host_scan": times[2] * 1e3,
                                           "total": sum(times) * 1e3}
             rec["bit_identical_to_reference_kernel"] = bool(ref_keep.tolist() == keep[: int(num.item())].cpu().numpy().tolist())
+        if n <= 10000:
+            rec["us_kernel_only"] = graph_us(lambda: NO.nms_sorted(t, thr, 3))
         if n <= 20000:
             t0 = time.perf_counter()
             O.cpu_nms_baseline(b, thr, 3)
@@ -122,7 +190,8 @@ def main():
         want, _ = MO.match_labels(anchors, gt, cls, 0.5, 3)
         cpu_us = (time.perf_counter() - t0) * 1e6
         got = MU.anchor_match_device(a, g_, c_, 3, 0.01, 0.5)[0].cpu().numpy()
-        match[name] = {"A": A, "G": G, "us": us, "alg_bytes": alg, "gbs": alg / us / 1e3, "frac_hbm": alg / us / 1e3 / PEAKS["hbm_gbs"],
+        ko = graph_us(lambda: MU.anchor_match_device(a, g_, c_, 3, 0.01, 0.5))
+        match[name] = {"A": A, "G": G, "us": us, "us_kernel_only": ko, "frac_hbm_kernel_only": None if isinstance(ko, str) else alg / ko / 1e3 / PEAKS["hbm_gbs"], "alg_bytes": alg, "gbs": alg / us / 1e3, "frac_hbm": alg / us / 1e3 / PEAKS["hbm_gbs"],
                        "numpy_f64_host_us": cpu_us, "bit_identical_to_numpy": bool(np.array_equal(got, want))}
     out["anchor_matching"] = match
     print(json.dumps(out, indent=1))
