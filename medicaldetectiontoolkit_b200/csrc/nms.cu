@@ -64,13 +64,23 @@ __device__ __forceinline__ bool suppresses(const float *a, float Sa, const float
 constexpr int kMaskGroups = 4;
 
 template <int DIM>
+__device__ __forceinline__ bool suppresses_tile(const float *a, float Sa, const float4 *tile, int i, float thresh, bool fast) {
+    float b[6];
+    const float4 b0 = tile[(DIM == 3 ? 2 : 1) * i];   // one (3D: two) 128-bit broadcast loads per column box
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+    if (DIM == 3) { const float4 b1 = tile[2 * i + 1]; b[4] = b1.x; b[5] = b1.y; } else { b[4] = b[5] = 0.f; }
+    return suppresses<DIM>(a, Sa, b, thresh, fast);
+}
+
+template <int DIM>
 __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
                                                                     unsigned long long *__restrict__ mask, int col_blocks, int full) {
     constexpr int F = BoxF<DIM>::n;
+    constexpr int V = DIM == 3 ? 2 : 1;   // float4 slots per staged box
     const int row_blk = blockIdx.x;
     const int group = threadIdx.x / kTile, t = threadIdx.x % kTile;
     const int row_size = min(n - row_blk * kTile, kTile);
-    __shared__ float tile[kMaskGroups][kTile * F];
+    __shared__ float4 tile[kMaskGroups][kTile * V];
     const int cur = row_blk * kTile + t;
     const bool row_live = t < row_size;
     float a[F];
@@ -83,13 +93,30 @@ __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, flo
         const int col_blk = c0 + group;
         const bool live = col_blk < col_blocks;
         const int col_size = live ? min(n - col_blk * kTile, kTile) : 0;
-        for (int i = t; i < col_size * F; i += kTile) tile[group][i] = boxes[(size_t)col_blk * kTile * F + i];
+        if (t < col_size) {   // coordinates only (the score column is not needed), as 16-byte vectors
+            const float *src = boxes + (size_t)(col_blk * kTile + t) * F;
+            tile[group][V * t] = make_float4(src[0], src[1], src[2], src[3]);
+            if (DIM == 3) tile[group][V * t + 1] = make_float4(src[4], src[5], 0.f, 0.f);
+        }
         asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kTile) : "memory");   // group-local barrier
         if (live && row_live) {
             unsigned long long word = 0;
-            const int start = (row_blk == col_blk) ? t + 1 : 0;   // a box may only suppress LOWER-scored boxes of its own block
-            for (int i = start; i < col_size; ++i)
-                if (suppresses<DIM>(a, Sa, tile[group] + i * F, thresh, fast)) word |= 1ULL << i;
+            if (col_size == kTile && row_blk != col_blk) {
+                // the bulk of the triangle, unrolled by 16 (ncu showed the rolled loop issue-bound at ~59 instructions per pair; ~25 here)
+#pragma unroll 1
+                for (int q = 0; q < kTile / 16; ++q) {   // 16 pairs per trip: constant bit positions and shared-memory offsets
+                    const float4 *tq = tile[group] + q * 16 * V;
+                    unsigned int bits = 0;
+#pragma unroll
+                    for (int u = 0; u < 16; ++u)
+                        if (suppresses_tile<DIM>(a, Sa, tq, u, thresh, fast)) bits |= 1u << u;
+                    word |= (unsigned long long)bits << (16 * q);
+                }
+            } else {
+                const int start = (row_blk == col_blk) ? t + 1 : 0;   // a box may only suppress LOWER-scored boxes of its own block
+                for (int i = start; i < col_size; ++i)
+                    if (suppresses_tile<DIM>(a, Sa, tile[group], i, thresh, fast)) word |= 1ULL << i;
+            }
             mask[(size_t)cur * col_blocks + col_blk] = word;
         }
         asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(kTile) : "memory");

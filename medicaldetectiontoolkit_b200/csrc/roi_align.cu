@@ -194,128 +194,96 @@ __global__ void __launch_bounds__(256) roi_bwd_cl4(RoiGeom g, const float *__res
     }
 }
 
-// ---------------------------------------------------------------- channels-last, taps staged per CTA ----------------------------------------------------------------
+// ---------------------------------------------------------------- channels-last, one RoI (slice) per CTA ----------------------------------------------------------------
 // ncu of roi_fwd_cl4 (P2, 7x7x3, 1024 RoIs): 390 instructions per thread, issue slots 54 % busy, DRAM 10 %: every one of the C/4
-// threads of a bin repeats the index decomposition (five integer divisions), three sampling coordinates (a float division each) and the
-// 64-bit address arithmetic.  Here a CTA owns `nb = 256 / (C/4)` consecutive bins; one thread per (bin, axis) computes that axis' tap
-// once (element offsets of the two neighbours + the lerp weight) into shared memory, then one thread per (bin, 4 channels) only
-// combines offsets, issues its eight 128-bit loads and interpolates.  Expressions are the same as above, so results are bit-identical.
-constexpr int kTapThreads = 256;
+// threads of a bin repeats the index decomposition (five integer divisions), three sampling coordinates (a float division each) and
+// the 64-bit address arithmetic; staging those per group of bins only moved the cost into a serial chain per group (24 us for the
+// 38 MB P2 map and for the 4.7 MB P3 map alike).  But the taps of an RoI are SEPARABLE: ch + cw + cz values (17 for 7x7x3), not
+// 3 per bin.  A CTA therefore owns one RoI (or a slice of its bins when the crop is large): ch+cw+cz threads compute one tap each
+// (neighbour offsets + lerp weight; box and box_ind loads are independent of each other), one pass fills a per-bin table (packed tap
+// indices + output offset), and then all 256 threads stream (bin, 4-channel) items: table lookups, eight 128-bit gathers, lerp, one
+// 128-bit store - no divisions and no barrier in the loop.  Expressions are those of roi_fwd_cl4 / roi_bwd_cl4: bit-identical results.
+constexpr int kRoiThreads = 256;
+constexpr int kMaxCropDim = 64;       // per axis, for the shared-memory tap tables
+constexpr int kMaxBinsPerCta = 1024;  // bins per CTA slice (12 KB of tables)
 
-struct TapSmem {
-    int lo[3][kTapThreads], hi[3][kTapThreads];   // element offsets (tap index x axis stride) inside one batch item
-    float lerp[3][kTapThreads];
-    int b[kTapThreads];                           // batch index, -1 = invalid box_ind (crop is zeros / no gradient)
-    long long out[kTapThreads];                   // element offset of the bin's channel vector in the crops tensor
+struct RoiTables {
+    int lo[3][kMaxCropDim], hi[3][kMaxCropDim];   // element offsets (tap index x axis stride) inside one batch item
+    float lerp[3][kMaxCropDim];
+    long long out[kMaxBinsPerCta];                // element offset of the bin's channel vector in the crops tensor
+    int yxz[kMaxBinsPerCta];                      // y | x << 8 | z << 16
 };
 
-template <int DIM>
-__device__ __forceinline__ void stage_taps(const RoiGeom &g, const float *__restrict__ boxes, const int *__restrict__ box_ind, unsigned bin0,
-                                           unsigned total_bins, int nb, TapSmem &s) {
-    const int t = threadIdx.x;
-    if (t >= nb * DIM) return;
-    const int bl = t / DIM, axis = t - bl * DIM;
-    const unsigned bin = bin0 + bl;
-    if (bin >= total_bins) return;
-    unsigned r = bin;
-    const int z = r % (unsigned)g.cz; r /= (unsigned)g.cz;
-    const int x = r % (unsigned)g.cw; r /= (unsigned)g.cw;
-    const int y = r % (unsigned)g.ch; r /= (unsigned)g.ch;
-    const int n = (int)r;
+template <int DIM, bool BWD>
+__global__ void __launch_bounds__(kRoiThreads) roi_cl4_per_roi(RoiGeom g, const float *__restrict__ src, const float *__restrict__ boxes,
+                                                              const int *__restrict__ box_ind, float *__restrict__ dst, int bins_per_slice) {
+    __shared__ RoiTables s;
+    const int n = blockIdx.x, tid = threadIdx.x;
+    const int P = g.ch * g.cw * g.cz;
+    const int bin0 = blockIdx.y * bins_per_slice, nbins = min(P - bin0, bins_per_slice);
     const int b_in = box_ind[n];
     const bool valid = b_in >= 0 && b_in < g.batch;
-    if (axis == 0) {
-        s.b[bl] = valid ? b_in : -1;
-        s.out[bl] = n * g.os[0] + y * g.os[2] + x * g.os[3] + z * g.os[4];
+    if (valid && tid < g.ch + g.cw + (DIM == 3 ? g.cz : 0)) {   // one tap per thread
+        const float *bx = boxes + (size_t)n * (2 * DIM);
+        Tap tp; int64_t stride; int axis, o;
+        if (tid < g.ch)             { axis = 0; o = tid;               tp = make_tap(sample_coord(bx[0], bx[2], o, g.ch, g.H)); stride = g.is[2]; }
+        else if (tid < g.ch + g.cw) { axis = 1; o = tid - g.ch;        tp = make_tap(sample_coord(bx[1], bx[3], o, g.cw, g.W)); stride = g.is[3]; }
+        else                        { axis = 2; o = tid - g.ch - g.cw; tp = make_tap(sample_coord(bx[4], bx[5], o, g.cz, g.Z)); stride = g.is[4]; }
+        s.lo[axis][o] = (int)(tp.lo * stride);
+        s.hi[axis][o] = (int)(tp.hi * stride);
+        s.lerp[axis][o] = tp.lerp;
     }
-    if (!valid) return;
-    const float *bx = boxes + (size_t)n * (2 * DIM);
-    Tap tp;
-    int64_t stride;
-    if (axis == 0)      { tp = make_tap(sample_coord(bx[0], bx[2], y, g.ch, g.H)); stride = g.is[2]; }
-    else if (axis == 1) { tp = make_tap(sample_coord(bx[1], bx[3], x, g.cw, g.W)); stride = g.is[3]; }
-    else                { tp = make_tap(sample_coord(bx[4], bx[5], z, g.cz, g.Z)); stride = g.is[4]; }
-    s.lo[axis][bl] = (int)(tp.lo * stride);
-    s.hi[axis][bl] = (int)(tp.hi * stride);
-    s.lerp[axis][bl] = tp.lerp;
-}
-
-// Persistent, software-pipelined: with one bin group per CTA the kernel was bound by the dependent chain box_ind -> box -> taps ->
-// gather -> store times the number of CTA waves (same 24-26 us for the 38 MB P2 map and the 4.7 MB P3 map).  Each CTA now walks
-// several groups and computes the taps of its NEXT group into the other shared-memory buffer while the gathers of the current group
-// are in flight, so the two latencies overlap instead of adding up.
-template <int DIM, bool BWD>
-__global__ void __launch_bounds__(kTapThreads) roi_cl4_pipe(RoiGeom g, const float *__restrict__ src, const float *__restrict__ boxes,
-                                                           const int *__restrict__ box_ind, float *__restrict__ dst, unsigned total_bins, int nb,
-                                                           unsigned ngroups) {
-    __shared__ TapSmem s[2];
-    const int C4 = g.C >> 2;
-    const int bl = threadIdx.x / C4, c4 = threadIdx.x - bl * C4;
-    unsigned grp = blockIdx.x;
-    if (grp >= ngroups) return;
-    stage_taps<DIM>(g, boxes, box_ind, grp * (unsigned)nb, total_bins, nb, s[0]);
+    for (int i = tid; i < nbins; i += kRoiThreads) {
+        unsigned r = bin0 + i;
+        const int z = r % (unsigned)g.cz; r /= (unsigned)g.cz;
+        const int x = r % (unsigned)g.cw; r /= (unsigned)g.cw;
+        const int y = (int)r;
+        s.yxz[i] = y | (x << 8) | (z << 16);
+        s.out[i] = n * g.os[0] + y * g.os[2] + x * g.os[3] + z * g.os[4];
+    }
     __syncthreads();
-    for (int cur = 0; grp < ngroups; grp += gridDim.x, cur ^= 1) {
-        const TapSmem &t = s[cur];
-        const bool live = bl < nb && grp * (unsigned)nb + bl < total_bins;
-        const int b = live ? t.b[bl] : -1;
-        const unsigned nxt = grp + gridDim.x;
-        if (!BWD) {
-            float4 tl[2], tr[2], bl_[2], br[2];
-            float ly = 0.f, lx = 0.f, lz = 0.f;
-            if (b >= 0) {
-                const float *p = src + b * g.is[0] + 4 * c4;
-                const int ylo = t.lo[0][bl], yhi = t.hi[0][bl], xlo = t.lo[1][bl], xhi = t.hi[1][bl];
-                ly = t.lerp[0][bl]; lx = t.lerp[1][bl];
-                if (DIM == 3) lz = t.lerp[2][bl];
+    const int C4 = g.C >> 2;
+    const int items = nbins * C4;
+    int bl = tid / C4, c4 = tid - bl * C4;                        // item -> (bin, channel group), advanced without divisions
+    const int dq = kRoiThreads / C4, dr = kRoiThreads - dq * C4;
+    const float *img = BWD ? nullptr : src + (valid ? b_in : 0) * g.is[0];
+    float *gim = BWD ? dst + (valid ? b_in : 0) * g.is[0] : nullptr;
+    for (int item = tid; item < items; item += kRoiThreads) {
+        const long long out_off = s.out[bl];
+        if (!valid) {
+            if (!BWD) *(reinterpret_cast<float4 *>(dst + out_off) + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int pk = s.yxz[bl];
+            const int y = pk & 255, x = (pk >> 8) & 255, z = pk >> 16;
+            const int ylo = s.lo[0][y], yhi = s.hi[0][y], xlo = s.lo[1][x], xhi = s.hi[1][x];
+            const float ly = s.lerp[0][y], lx = s.lerp[1][x], lz = (DIM == 3) ? s.lerp[2][z] : 0.f;
+            if (!BWD) {
+                const float *p = img + 4 * c4;
+                float4 v[2];
 #pragma unroll
                 for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
-                    const int oz = (DIM == 3) ? (kz ? t.hi[2][bl] : t.lo[2][bl]) : 0;
-                    tl[kz] = __ldg(reinterpret_cast<const float4 *>(p + ylo + xlo + oz));
-                    tr[kz] = __ldg(reinterpret_cast<const float4 *>(p + ylo + xhi + oz));
-                    bl_[kz] = __ldg(reinterpret_cast<const float4 *>(p + yhi + xlo + oz));
-                    br[kz] = __ldg(reinterpret_cast<const float4 *>(p + yhi + xhi + oz));
-                }
-            }
-            const long long out_off = live ? t.out[bl] : 0;
-            if (nxt < ngroups) stage_taps<DIM>(g, boxes, box_ind, nxt * (unsigned)nb, total_bins, nb, s[cur ^ 1]);   // overlaps the gathers
-            if (live) {
-                float4 *out = reinterpret_cast<float4 *>(dst + out_off) + c4;
-                if (b < 0) {
-                    *out = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-                    float4 v[2];
-#pragma unroll
-                    for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
-#define MDT_LERP2(f) { const float top = tl[kz].f + (tr[kz].f - tl[kz].f) * lx, bot = bl_[kz].f + (br[kz].f - bl_[kz].f) * lx; v[kz].f = top + (bot - top) * ly; }
-                        MDT_LERP2(x) MDT_LERP2(y) MDT_LERP2(z) MDT_LERP2(w)
+                    const int oz = (DIM == 3) ? (kz ? s.hi[2][z] : s.lo[2][z]) : 0;
+                    const float4 tl = __ldg(reinterpret_cast<const float4 *>(p + ylo + xlo + oz));
+                    const float4 tr = __ldg(reinterpret_cast<const float4 *>(p + ylo + xhi + oz));
+                    const float4 bl_ = __ldg(reinterpret_cast<const float4 *>(p + yhi + xlo + oz));
+                    const float4 br = __ldg(reinterpret_cast<const float4 *>(p + yhi + xhi + oz));
+#define MDT_LERP2(f) { const float top = tl.f + (tr.f - tl.f) * lx, bot = bl_.f + (br.f - bl_.f) * lx; v[kz].f = top + (bot - top) * ly; }
+                    MDT_LERP2(x) MDT_LERP2(y) MDT_LERP2(z) MDT_LERP2(w)
 #undef MDT_LERP2
-                    }
-                    float4 o = v[0];
-                    if (DIM == 3) {
-                        o.x = v[0].x + (v[1].x - v[0].x) * lz; o.y = v[0].y + (v[1].y - v[0].y) * lz;
-                        o.z = v[0].z + (v[1].z - v[0].z) * lz; o.w = v[0].w + (v[1].w - v[0].w) * lz;
-                    }
-                    *out = o;
                 }
-            }
-        } else {
-            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-            int ylo = 0, yhi = 0, xlo = 0, xhi = 0, zlo = 0, zhi = 0;
-            float ly = 0.f, lx = 0.f, lz = 0.f;
-            if (b >= 0) {
-                gv = __ldg(reinterpret_cast<const float4 *>(src + t.out[bl]) + c4);
-                ylo = t.lo[0][bl]; yhi = t.hi[0][bl]; xlo = t.lo[1][bl]; xhi = t.hi[1][bl];
-                ly = t.lerp[0][bl]; lx = t.lerp[1][bl];
-                if (DIM == 3) { zlo = t.lo[2][bl]; zhi = t.hi[2][bl]; lz = t.lerp[2][bl]; }
-            }
-            if (nxt < ngroups) stage_taps<DIM>(g, boxes, box_ind, nxt * (unsigned)nb, total_bins, nb, s[cur ^ 1]);   // overlaps the gradient load
-            if (b >= 0) {
-                float *p = dst + b * g.is[0] + 4 * c4;
+                float4 o = v[0];
+                if (DIM == 3) {
+                    o.x = v[0].x + (v[1].x - v[0].x) * lz; o.y = v[0].y + (v[1].y - v[0].y) * lz;
+                    o.z = v[0].z + (v[1].z - v[0].z) * lz; o.w = v[0].w + (v[1].w - v[0].w) * lz;
+                }
+                *(reinterpret_cast<float4 *>(dst + out_off) + c4) = o;
+            } else {
+                const float4 gv = __ldg(reinterpret_cast<const float4 *>(src + out_off) + c4);
+                float *p = gim + 4 * c4;
 #pragma unroll
                 for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
                     const float wz = (DIM == 3) ? (kz ? lz : 1 - lz) : 1.f;
-                    const int oz = (DIM == 3) ? (kz ? zhi : zlo) : 0;
+                    const int oz = (DIM == 3) ? (kz ? s.hi[2][z] : s.lo[2][z]) : 0;
 #pragma unroll
                     for (int ky = 0; ky < 2; ++ky) {
                         const float wy = ky ? ly : 1 - ly;
@@ -331,25 +299,27 @@ __global__ void __launch_bounds__(kTapThreads) roi_cl4_pipe(RoiGeom g, const flo
                 }
             }
         }
-        __syncthreads();   // s[cur ^ 1] is complete; every read of s[cur] above is done
+        bl += dq; c4 += dr;
+        if (c4 >= C4) { c4 -= C4; ++bl; }
     }
 }
 
-template <int DIM, bool BWD>
-static int pipe_grid(unsigned ngroups) {
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, roi_cl4_pipe<DIM, BWD>, kTapThreads, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
-    }
-    const long long cap = (long long)num_sms() * per_sm;
-    return (int)(ngroups < cap ? ngroups : cap);
-}
-
-// the staged kernels keep tap offsets in 32 bits and one (bin, 4 channels) element per thread
-static bool taps_ok(const RoiGeom &g, long long total_bins) {
-    if ((g.C >> 2) > kTapThreads || total_bins >= (1LL << 31)) return false;
+// the per-RoI kernels keep tap offsets in 32 bits, tap tables of 64 entries per axis and <= 256 channel groups
+static bool per_roi_ok(const RoiGeom &g) {
+    if ((g.C >> 2) > kRoiThreads || g.ch > kMaxCropDim || g.cw > kMaxCropDim || g.cz > kMaxCropDim) return false;
     const long long span = (long long)g.H * g.is[2] + (long long)g.W * g.is[3] + (long long)g.Z * g.is[4];
     return span < (1LL << 31);
+}
+
+// slices per RoI: ~1500 (bin, 4-channel) items per CTA keeps the table pass short and gives the scheduler several CTAs per SM
+static void per_roi_grid(const RoiGeom &g, dim3 &grid, int &bins_per_slice) {
+    const int P = g.ch * g.cw * g.cz, C4 = g.C >> 2;
+    int bins = 1536 / C4;
+    if (bins < 1) bins = 1;
+    if (bins > kMaxBinsPerCta) bins = kMaxBinsPerCta;
+    if (bins > P) bins = P;
+    bins_per_slice = bins;
+    grid = dim3((unsigned)g.num_boxes, (unsigned)ceil_div(P, bins), 1);
 }
 
 static bool cl4_ok(const RoiGeom &g, const void *img, const void *crop) {
@@ -378,11 +348,10 @@ static int roi_forward(const float *image, const int64_t *is, const float *boxes
     for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = os[k]; }
     const long long total = (long long)num_boxes * C * ch * cw * cz;
     const bool small = fits_u32(total);
-    const long long total_bins = (long long)num_boxes * ch * cw * cz;
-    if (cl4_ok(g, image, crops) && taps_ok(g, total_bins)) {
-        const int nb = kTapThreads / (C >> 2);
-        const unsigned ngroups = (unsigned)ceil_div(total_bins, (long long)nb);
-        roi_cl4_pipe<DIM, false><<<pipe_grid<DIM, false>(ngroups), kTapThreads, 0, st>>>(g, image, boxes, box_ind, crops, (unsigned)total_bins, nb, ngroups);
+    if (cl4_ok(g, image, crops) && per_roi_ok(g)) {
+        dim3 grid; int bins;
+        per_roi_grid(g, grid, bins);
+        roi_cl4_per_roi<DIM, false><<<grid, kRoiThreads, 0, st>>>(g, image, boxes, box_ind, crops, bins);
     } else if (cl4_ok(g, image, crops)) {
         if (small) roi_fwd_cl4<DIM, unsigned><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
         else       roi_fwd_cl4<DIM, long long><<<grid_for(total / 4, 256), 256, 0, st>>>(g, image, boxes, box_ind, crops, total / 4);
@@ -409,11 +378,10 @@ static int roi_backward(const float *grads, const int64_t *gs, const float *boxe
     for (int k = 0; k < DIM + 2; ++k) { g.is[k] = is[k]; g.os[k] = gs[k]; }
     const long long total = (long long)num_boxes * C * ch * cw * cz;
     const bool small = fits_u32(total);
-    const long long total_bins = (long long)num_boxes * ch * cw * cz;
-    if (cl4_ok(g, gimg, grads) && taps_ok(g, total_bins)) {
-        const int nb = kTapThreads / (C >> 2);
-        const unsigned ngroups = (unsigned)ceil_div(total_bins, (long long)nb);
-        roi_cl4_pipe<DIM, true><<<pipe_grid<DIM, true>(ngroups), kTapThreads, 0, st>>>(g, grads, boxes, box_ind, gimg, (unsigned)total_bins, nb, ngroups);
+    if (cl4_ok(g, gimg, grads) && per_roi_ok(g)) {
+        dim3 grid; int bins;
+        per_roi_grid(g, grid, bins);
+        roi_cl4_per_roi<DIM, true><<<grid, kRoiThreads, 0, st>>>(g, grads, boxes, box_ind, gimg, bins);
     } else if (cl4_ok(g, gimg, grads)) {
         if (small) roi_bwd_cl4<DIM, unsigned><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
         else       roi_bwd_cl4<DIM, long long><<<grid_for(total / 4, 256), 256, 0, st>>>(g, grads, boxes, box_ind, gimg, total / 4);
