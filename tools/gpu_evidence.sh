@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 timeout 900 python -m pytest tests -q -m gpu -x --timeout 600 --durations=12 2>&1 | tail -30 > gpurun_out/pytest_gpu.txt; cut -c1-200 gpurun_out/pytest_gpu.txt
 timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 | tee gpurun_out/smoke.txt
-timeout 400 python tools/microbench.py > gpurun_out/microbench.json 2> gpurun_out/microbench.err; tail -2 gpurun_out/microbench.err
+[ -z "$SKIP_MICRO" ] && timeout 400 python tools/microbench.py > gpurun_out/microbench.json 2> gpurun_out/microbench.err; tail -2 gpurun_out/microbench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
