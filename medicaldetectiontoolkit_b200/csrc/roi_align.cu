@@ -207,8 +207,6 @@ constexpr int kRoiThreads = 256;
 constexpr int kMaxCropDim = 64;       // per axis, for the shared-memory tap tables
 constexpr int kMaxBinsPerCta = 1024;  // bins per CTA slice (12 KB of tables)
 
-__device__ __forceinline__ void prefetch_l2(const float *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 struct RoiTables {
     int lo[3][kMaxCropDim], hi[3][kMaxCropDim];   // element offsets (tap index x axis stride) inside one batch item
     float lerp[3][kMaxCropDim];
@@ -250,26 +248,6 @@ __global__ void __launch_bounds__(kRoiThreads) roi_cl4_per_roi(RoiGeom g, const 
     const int dq = kRoiThreads / C4, dr = kRoiThreads - dq * C4;
     const float *img = BWD ? nullptr : src + (valid ? b_in : 0) * g.is[0];
     float *gim = BWD ? dst + (valid ? b_in : 0) * g.is[0] : nullptr;
-    if (!BWD && valid) {
-        // Pass 0: L2 prefetch of every corner this thread will gather.  ncu showed the gather loop waiting on DRAM latency with only the
-        // eight loads of ONE item in flight per thread (long-scoreboard stalls 12x issue, issue slots 25 % busy); prefetches need no
-        // destination registers, so the whole slice is requested at once and the loop below runs at L2 latency.
-        int pb = bl, pc = c4;
-        for (int item = tid; item < items; item += kRoiThreads) {
-            const int pk = s.yxz[pb];
-            const int y = pk & 255, x = (pk >> 8) & 255, z = pk >> 16;
-            const float *p = img + 4 * pc;
-            const int ylo = s.lo[0][y], yhi = s.hi[0][y], xlo = s.lo[1][x], xhi = s.hi[1][x];
-#pragma unroll
-            for (int kz = 0; kz < (DIM == 3 ? 2 : 1); ++kz) {
-                const int oz = (DIM == 3) ? (kz ? s.hi[2][z] : s.lo[2][z]) : 0;
-                prefetch_l2(p + ylo + xlo + oz); prefetch_l2(p + ylo + xhi + oz);
-                prefetch_l2(p + yhi + xlo + oz); prefetch_l2(p + yhi + xhi + oz);
-            }
-            pb += dq; pc += dr;
-            if (pc >= C4) { pc -= C4; ++pb; }
-        }
-    }
     for (int item = tid; item < items; item += kRoiThreads) {
         const long long out_off = s.out[bl];
         if (!valid) {
