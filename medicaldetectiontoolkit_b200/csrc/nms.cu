@@ -7,7 +7,7 @@
 //
 // Arithmetic pinning: nvcc (default -fmad=true) compiles the reference's `Sa + Sb - interS` as fma(sb_hw, sb_d, Sa) - interS
 // (checked in the sm_100a SASS of the unmodified reference file). We spell that sequence with explicit intrinsics so that neither
-// our compiler flags nor the CPU oracle (oracle/nms_oracle.c uses fmaf) can drift from it.
+// our compiler flags nor the CPU oracle (oracle/mdt_oracle.c uses fmaf) can drift from it.
 #include <stdlib.h>
 
 #include "mdt_common.cuh"
@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, flo
     }
 }
 
-// Greedy reduction on one CTA — the exact recurrence of nms_cuda.c:47-58 with remv (the suppression bitmap) in shared memory.
-// Boxes are consumed 64 at a time:
+// Greedy reduction on one CTA (first version; selected by MDT_NMS_SCAN=1 for A/B runs, the default is nms_scan_grid_kernel below) —
+// the exact recurrence of nms_cuda.c:47-58 with remv (the suppression bitmap) in shared memory.  Boxes are consumed 64 at a time:
 //   (1) one thread resolves the 64 keep decisions of the block from the 64 diagonal mask words (registers / shared memory only);
 //   (2) the 1024 threads, arranged as 64 rows x 16 word-lanes, OR the mask rows of the boxes just kept into remv: every thread streams
 //       its strided share of a row with independent 8-byte loads (several in flight) and touches remv only for non-zero words.
-// The diagonal words of the NEXT block do not depend on remv and are prefetched during (2).
+// Runs of blocks whose boxes are all suppressed already are skipped with one barrier per run.
 constexpr int kScanThreads = 1024;
 constexpr int kScanLanes = kScanThreads / kTile;   // 16 word-lanes per row
 
