@@ -100,7 +100,10 @@ def run_reference(args):
     sample = "%d full train step(s) of %d patch(es) %s (forward+detections+matching+losses+backward+Adam), fp32, torch CPU" % (len(times), b, "x".join(map(str, patch)))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus, "steps": len(times),
             "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "lidc_exp 3D Retina U-Net, synthetic 1-ch %s patches, batch %d" % ("x".join(map(str, patch)), b)},
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: lidc_exp 3D Retina U-Net, synthetic 1-ch %s patches, batch %d per GPU" % ("x".join(map(str, patch)), args.batch),
+                       "global_batch": b, "parallelism": "host cores (%d threads)" % used, "optimizer": "Adam lr 1e-4",
+                       "sample": "each step = one full train step of %d patch(es) on the CPU" % b},
             "cpu_baseline": {"value": val, "unit": "patches/s", "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
