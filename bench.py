@@ -109,6 +109,32 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def make_roofline(step_flops, conv_ms, n_conv_calls, ms_step, dom, peak_tf, peaks_measured):
+    """roofline object of the JSON line.  Top level = the dominant kernel launch (the heaviest forward conv: flops of that launch / its
+    CUDA-event duration measured live in the timed region, DRAM traffic from its ncu capture); `all_conv_launches` = the same ratio over
+    every conv call of the step.  dom = (flops, ms, tag, calls_per_step) or None; pure function (tests/test_bench_cpu.py)."""
+    if not conv_ms:
+        return None
+    src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks_measured else "fallback 1.4 PF sustained (of fallback)"
+    ach = step_flops / (conv_ms / 1e3) / 1e12
+    agg = {"kernel": "conv3d fprop+dgrad+wgrad (all layers, %d launches/step)" % round(n_conv_calls), "achieved": ach, "unit": "TFLOP/s",
+           "frac": ach / peak_tf, "algorithmic_flops_per_step": step_flops, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step}
+    if dom is None:
+        roof = {"bound": "tensor", "kernel": agg["kernel"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None}
+    else:
+        fl, ms_k, tag, _ = dom
+        roof = {"bound": "tensor",
+                "kernel": "conv_tc_kernel fprop %d->%d k%s on %s (incl. its operand split/pack launches)" % (tag[1][1], tag[2][0], "x".join(map(str, tag[2][2:])), "x".join(map(str, tag[1]))),
+                "achieved": fl / ms_k / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": fl / ms_k / 1e9 / peak_tf,
+                "traffic": 1.655e9 if tuple(tag[1]) == (2, 36, 128, 128, 128) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/r01_ncu_ops_summary.txt, conv_tc_kernel 36->36: 1.074 GB + 0.584 GB; algorithmic minimum 4*(in+out) = 1.21 GB)",
+                "algorithmic_flops": fl, "ms": ms_k,
+                "note": "fp32-faithful split-bf16 arithmetic issues 3 bf16 MMAs per algorithmic MAC: at most 1/3 of the bf16 peak by construction"}
+    roof["peak_source"] = src
+    roof["all_conv_launches"] = agg
+    return roof
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -250,20 +276,7 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     step_flops = 3.0 * fwd_flops
-    roof = None
-    if conv_ms:
-        ach = step_flops / (conv_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv3d fprop+dgrad+wgrad (all layers, %d launches/step)" % round(n_conv_calls), "achieved": ach,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PF sustained (of fallback)",
-                "algorithmic_flops_per_step": step_flops, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms_dev / args.steps)}
-        if dom is not None:
-            fl, ms_k, tag, _ = dom
-            roof["dominant_launch"] = {
-                "kernel": "conv_tc_kernel fprop %d->%d k%s on %s (incl. its operand split/pack launches)" % (tag[1][1], tag[2][0], "x".join(map(str, tag[2][2:])), "x".join(map(str, tag[1]))),
-                "algorithmic_flops": fl, "ms": ms_k, "achieved": fl / ms_k / 1e9, "unit": "TFLOP/s", "frac": fl / ms_k / 1e9 / peak_tf,
-                "traffic": 1.655e9 if tuple(tag[1]) == (2, 36, 128, 128, 128) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/r01_ncu_conv_tc_fprop_p0_36.txt): 1.074 GB + 0.581 GB; algorithmic minimum 4*(in+out) = 1.21 GB"}
+    roof = make_roofline(step_flops, conv_ms, n_conv_calls if conv_ms else 0, ms_dev / args.steps, dom if conv_ms else None, peak_tf, bool(peaks))
     h2d = sum(int(hb['data'].numel() * hb['data'].element_size() + hb['seg'].numel() * hb['seg'].element_size()) for hb in host_batches[:1])
     d2h = int(args.batch * np.prod(patch)) + 60 * 9 * 4 + 5 * 4  # seg_preds uint8 + detections + loss scalars
     line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
