@@ -37,8 +37,15 @@ def _offsets(red):
         off += p.numel()
 
 
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:   # a fixed port can still be in TIME_WAIT from an earlier run
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 def test_flat_grad_allreduce_gloo_world2():
-    world, port = 2, 29611
+    world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
