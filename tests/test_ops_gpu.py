@@ -33,7 +33,7 @@ def _keep(boxes, thr, dim):
 # ----------------------------------------------------------------------------------------------------------------------------------- NMS
 @pytest.mark.parametrize("dim", [2, 3])
 def test_nms_vs_oracle_small_and_edges(dim):
-    for n in [0, 1, 2, 63, 64, 65, 129, 1000]:
+    for n in [0, 1, 2, 63, 64, 65, 129, 1000, 1024, 1025, 2049, 2112]:   # incl. the 16-block chunk / first-worker boundaries of the grid scan
         for thr in [0.7, 0.5, 1e-5]:
             for rounded in (True, False):
                 boxes = O.synth_boxes(n, dim, seed=17 * n + dim, rounded=rounded, extent=48.0 if n > 100 else 24.0)
