@@ -147,8 +147,8 @@ int conv_stem_wgrad(const ConvGeom &g, const float *x, const float *dy, float *d
     long long blocks = (long long)num_sms() * 8;
     if (blocks > nlines) blocks = nlines;
     const size_t smem = ((size_t)g.ow * g.cout + (size_t)g.kd * g.kh * (g.ow + g.kw - 1) * g.cin) * sizeof(float);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    static bool attr[kMaxDevices] = {};
+    if (!ensure_smem_attr(stem_wgrad_kernel, 96 * 1024, attr)) return MDT_EDRIVER;
     stem_wgrad_kernel<<<(unsigned)blocks, 256, smem, st>>>(g, x, dy, dw, ceil_div<long long>(nlines, blocks));
     int rc = launch_status();
     if (rc) return rc;

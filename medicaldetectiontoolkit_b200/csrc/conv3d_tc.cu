@@ -477,8 +477,8 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     if (conv_tc_pair_wanted(g, pl, p, pass)) return conv_tc_pair_launch(g, pl, p, tmA, wp, T, st);   // experimental CTA-pair kernel (MDT_TC_PAIR=1)
 
     const size_t smem = (size_t)p.D * p.stage_bytes + 1024;
-    static bool attr = false;
-    if (!attr) { if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER; attr = true; }
+    static bool attr[kMaxDevices] = {};
+    if (!ensure_smem_attr(conv_tc_kernel, 220 * 1024, attr)) return MDT_EDRIVER;
     dim3 grid((unsigned)((long long)g.n * pl.RD * p.tiles_h * p.tiles_w), pl.n_tiles_n);
     conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);
     return launch_status();

@@ -305,11 +305,8 @@ int conv_tc_pair_launch(const ConvGeom &g, const TcPlan &pl, const TcConvParams 
     void *wp = const_cast<void *>(packed_weights);
     if (!encode_bf16_tmap(&tmBx, wp, 4, bdims, bstr, box_x, pl.swz) || !encode_bf16_tmap(&tmBy, wp, 4, bdims, bstr, box_y, pl.swz)) return MDT_EDRIVER;
     const size_t smem = (size_t)p.stage_bytes + 1024;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER;
-        attr = true;
-    }
+    static bool attr[kMaxDevices] = {};
+    if (!ensure_smem_attr(conv_tc_pair_kernel, 220 * 1024, attr)) return MDT_EDRIVER;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((long long)g.n * pl.RD * p.tiles_h * p.tiles_w), pl.n_tiles_n);
     cfg.blockDim = dim3(kTcThreads);

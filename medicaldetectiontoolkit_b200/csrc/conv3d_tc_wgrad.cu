@@ -390,11 +390,8 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     const size_t tail = walk > (size_t)p.stage_bytes ? walk - p.stage_bytes : 0;
     const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + tail;
     if (smem > 218 * 1024) return MDT_EUNSUPPORTED;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) return MDT_EDRIVER;
-        attr = true;
-    }
+    static bool attr[kMaxDevices] = {};
+    if (!ensure_smem_attr(conv_tc_wgrad_kernel, 220 * 1024, attr)) return MDT_EDRIVER;
     dim3 grid((unsigned)(w.groups * p.splits), w.mtiles);
     conv_tc_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(tmY, tmX, p);
     if ((rc = launch_status())) return rc;

@@ -32,6 +32,19 @@ inline int num_sms() {
 template <typename T>
 __host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
 
+// The opt-in dynamic shared-memory size is a PER-DEVICE function attribute: a process that drives several GPUs must set it on each.
+// `done` is the call site's table (one per kernel).
+constexpr int kMaxDevices = 64;
+template <typename K>
+inline bool ensure_smem_attr(K kernel, int bytes, bool (&done)[kMaxDevices]) {
+    int dev = 0;
+    const bool tracked = cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < kMaxDevices;
+    if (tracked && done[dev]) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    if (tracked) done[dev] = true;
+    return true;
+}
+
 inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace mdt

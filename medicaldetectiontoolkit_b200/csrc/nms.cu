@@ -456,11 +456,8 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
     if (scan_variant() == 1) {
         const size_t smem = (size_t)cb * sizeof(unsigned long long);
         if (smem > 200 * 1024) return MDT_EUNSUPPORTED;  // N <= 1.6 M boxes
-        static bool attr_set = false;
-        if (!attr_set) {
-            if (cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return MDT_EUNSUPPORTED;
-            attr_set = true;
-        }
+        static bool attr_set[kMaxDevices] = {};
+        if (!ensure_smem_attr(nms_scan_kernel, 200 * 1024, attr_set)) return MDT_EUNSUPPORTED;
         nms_scan_kernel<<<1, kScanThreads, smem, st>>>(n, cb, mask, keep, num_out);
         return launch_status();
     }
@@ -469,11 +466,8 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
     cudaError_t e = cudaMemsetAsync(remv_g, 0, (size_t)cb * sizeof(unsigned long long) + sizeof(ScanCtl), st);
     if (e != cudaSuccess) return (int)e;
     const size_t smem = (size_t)kChunkRows * kChunkPitch * sizeof(unsigned long long);
-    static bool grid_attr_set = false;
-    if (!grid_attr_set) {
-        if (cudaFuncSetAttribute(nms_scan_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return MDT_EUNSUPPORTED;
-        grid_attr_set = true;
-    }
+    static bool grid_attr_set[kMaxDevices] = {};
+    if (!ensure_smem_attr(nms_scan_grid_kernel, (int)smem, grid_attr_set)) return MDT_EUNSUPPORTED;
     // CTA 0 + workers, one CTA per SM at most (cooperative launch: all co-resident); a ticket starts two chunks ahead of the chunk that
     // issues it, so up to 32 blocks need no worker at all; ~8 bitmap words per worker and ticket at least
     int grid = cb > 2 * kChunkBlocks ? 1 + ceil_div(cb - 2 * kChunkBlocks, 8) : 1;
