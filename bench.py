@@ -168,6 +168,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not mix with the one JSON line on stdout
         dist.init_process_group("nccl", device_id=dev)
     lib = L.load()
     C.DEFAULT_PRECISION = args.precision
