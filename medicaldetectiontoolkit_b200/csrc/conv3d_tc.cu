@@ -474,8 +474,6 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     }
     p.a_tx_bytes = rows_loaded * pl.swz;   // per plane; expect_tx must equal the bytes the TMA boxes deliver
 
-    if (conv_tc_pair_wanted(g, pl, p, pass)) return conv_tc_pair_launch(g, pl, p, tmA, wp, T, st);   // experimental CTA-pair kernel (MDT_TC_PAIR=1)
-
     const size_t smem = (size_t)p.D * p.stage_bytes + 1024;
     static bool attr[kMaxDevices] = {};
     if (!ensure_smem_attr(conv_tc_kernel, 220 * 1024, attr)) return MDT_EDRIVER;

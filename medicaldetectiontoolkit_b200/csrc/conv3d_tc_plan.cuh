@@ -1,4 +1,4 @@
-// Plan + parameter block of the tcgen05 implicit-GEMM conv kernels (shared by conv3d_tc.cu and conv3d_tc_pair.cu).
+// Plan + parameter block of the tcgen05 implicit-GEMM conv kernels (conv3d_tc.cu).
 #pragma once
 #include <stdlib.h>
 
@@ -102,10 +102,5 @@ static inline bool plan_stages(const TcPlan &pl, int kw, int planes, int &CPS, i
     if (const char *e = getenv("MDT_TC_D")) { const int v = atoi(e); if (v >= 1 && v <= kTcMaxStages && v * stage <= budget) D = v; }
     return true;
 }
-
-// CTA-pair variant (conv3d_tc_pair.cu): experimental, selected by MDT_TC_PAIR=1 for shapes it supports; returns MDT_EUNSUPPORTED otherwise
-bool conv_tc_pair_wanted(const ConvGeom &g, const TcPlan &pl, const TcConvParams &p, int pass);
-int conv_tc_pair_launch(const ConvGeom &g, const TcPlan &pl, const TcConvParams &p, const CUtensorMap &tmA, const void *packed_weights, int T,
-                        cudaStream_t st);
 
 }  // namespace mdt

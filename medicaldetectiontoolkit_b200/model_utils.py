@@ -259,10 +259,52 @@ bbox_overlaps_2D = bbox_overlaps
 bbox_overlaps_3D = bbox_overlaps
 
 
+# Sampling mode of every stochastic draw on the path (SHEM pools, positive-roi sub-sampling): "random" = device RNG (the reference draws
+# from the CPU RNG: same distribution, different stream); "identity" = the permutation is the identity, i.e. the reference with
+# torch.randperm neutralised — the mode the reference-pinned parity tests run both sides in (tests/golden/make_model_golden.py).
+SAMPLING = "random"
+
+
+def randperm(n, device, generator=None):
+    """torch.randperm(n) of utils/model_utils.py:690 / models/mrcnn.py:532 on the device"""
+    if SAMPLING == "identity":
+        return torch.arange(n, device=device)
+    return torch.randperm(n, device=device, generator=generator)
+
+
+def rand_keys(k, device, generator=None):
+    """k sort keys in [0, 1): taking the j smallest keys of a masked subset == the first j entries of a random permutation of it"""
+    if SAMPLING == "identity":
+        return torch.arange(k, device=device, dtype=torch.float32) / max(k, 1)
+    return torch.rand(k, device=device, generator=generator)
+
+
 def shem(roi_probs_neg, negative_count, ohem_poolsize):
     """stochastic hard example mining (utils/model_utils.py:674-691): sample `negative_count` indices out of the
     `negative_count * ohem_poolsize` highest-scoring (max foreground probability) candidates; device randperm."""
     probs, order = roi_probs_neg[:, 1:].max(1)[0].sort(descending=True)
     select = min(ohem_poolsize * int(negative_count), order.shape[0])
     pool = order[:select]
-    return pool[torch.randperm(pool.shape[0], device=pool.device)[:negative_count]]
+    return pool[randperm(pool.shape[0], pool.device)[:negative_count]]
+
+
+def log2(x):
+    """utils/model_utils.py:658-663"""
+    return torch.log2(x)
+
+
+def get_one_hot_encoding(y, n_classes):
+    """numpy drop-in of utils/model_utils.py:785-799: y (b, 1, y, x, (z)) integer labels -> (b, n_classes, y, x, (z)) int32"""
+    y = np.asarray(y)
+    out = np.zeros((y.shape[0], n_classes) + tuple(y.shape[2:]), dtype='int32')
+    for c in range(n_classes):
+        out[:, c][y[:, 0] == c] = 1
+    return out
+
+
+def batch_dice(pred, y, false_positive_weight=1.0, smooth=1e-6):
+    """soft dice over the batch pseudo-volume, foreground classes only (utils/model_utils.py:833-858)"""
+    axes = (0,) + tuple(range(2, pred.dim()))
+    intersect = (pred * y).sum(axes)
+    denom = (false_positive_weight * pred + y).sum(axes)
+    return torch.mean(((2 * intersect + smooth) / (denom + smooth))[1:])

@@ -233,7 +233,7 @@ def detection_target_layer(batch_proposals, batch_mrcnn_class_scores, batch_gt_c
             negative_idx = torch.nonzero(roi_iou_max < (0.1 if dim == 2 else 0.01)).squeeze(1)
             if positive_idx.numel() > 0:
                 want = int(cf.train_rois_per_image * cf.roi_positive_ratio)
-                positive_idx = positive_idx[torch.randperm(positive_idx.numel(), device=dev)[:want]]
+                positive_idx = positive_idx[mutils.randperm(positive_idx.numel(), dev)[:want]]
                 positive_samples = positive_idx.numel()
                 positive_rois = proposals[positive_idx]
                 assign = overlaps[positive_idx].max(dim=1)[1]

@@ -71,9 +71,11 @@ def compute_class_loss(anchor_matches, class_pred_logits, shem_poolsize=20, max_
     """
     A = anchor_matches.shape[0]
     dev = class_pred_logits.device
-    k_pos = int(min(A, max_pos if max_pos is not None else 64))
     pos_flag = (anchor_matches > 0)
     n_pos = pos_flag.sum()
+    # max_pos is the caller's guarantee on the number of positives (the matching caps it at rpn_train_anchors_per_image // 2); without
+    # it the bound is read back from the device (one sync) so that the reference's signature stays lossless for any number of positives
+    k_pos = int(min(A, max_pos)) if max_pos is not None else max(1, int(n_pos.item()))
     # first k_pos positive indices in ascending order (stable): key = index where positive, A otherwise
     idx = torch.arange(A, device=dev)
     pos_idx = torch.topk(torch.where(pos_flag, idx, idx.new_full((), A)), k_pos, largest=False, sorted=True)[0]
@@ -93,7 +95,7 @@ def compute_class_loss(anchor_matches, class_pred_logits, shem_poolsize=20, max_
     pool_size = torch.minimum(shem_poolsize * negative_count, n_neg_total)   # model_utils.py:687
     in_pool = (torch.arange(k_pool, device=dev) < pool_size) & (pool_score >= 0)
     # sample `negative_count` of the pool without replacement: smallest random keys among pool members (== randperm(pool)[:n])
-    keys = torch.rand(k_pool, device=dev, generator=generator)
+    keys = mutils.rand_keys(k_pool, dev, generator)
     keys = torch.where(in_pool, keys, keys.new_full((), 2.0))
     k_neg = int(min(k_pool, k_pos))
     sel_key, sel = torch.topk(keys, k_neg, largest=False)
@@ -328,9 +330,4 @@ class net(nn.Module):
         return get_results(self.cf, img.shape, detections, seg_logits)
 
 
-def batch_dice(pred, y, false_positive_weight=1.0, smooth=1e-6):
-    """soft dice over the batch pseudo-volume, foreground classes only (utils/model_utils.py:833-858)"""
-    axes = (0,) + tuple(range(2, pred.dim()))
-    intersect = (pred * y).sum(axes)
-    denom = (false_positive_weight * pred + y).sum(axes)
-    return torch.mean(((2 * intersect + smooth) / (denom + smooth))[1:])
+batch_dice = mutils.batch_dice

@@ -152,30 +152,3 @@ def test_fused_backward_relu_residual_bias(cin, cout, sp):
         assert _rel(x.grad, xd.grad) < TOL
     d = C._desc(tuple(x.shape), tuple(w.shape), (1, 1, 1), (pad,) * 3, False, 0, 0)
     assert L.load().mdt_conv3d_backward_fused(d, int(cin > 1)) == (1 if cin > 4 else 0)    # fused tcgen05 path; the Cin<=4 stem uses the direct kernels
-
-
-@pytest.mark.skipif(os.environ.get("MDT_TEST_PAIR") != "1", reason="experimental CTA-pair (cta_group::2) conv kernel: opt in with MDT_TEST_PAIR=1")
-@pytest.mark.parametrize("cin,cout,k,stride,sp", [(36, 36, 3, 1, (4, 8, 128)), (18, 18, 3, 1, (3, 6, 128)), (18, 36, 3, (2, 2, 1), (4, 8, 128)),
-                                                    (18, 18, 7, (2, 2, 1), (8, 8, 128))])
-def test_pair_kernel_matches_default_path(cin, cout, k, stride, sp):
-    """conv3d_tc_pair.cu (MDT_TC_PAIR=1) must reproduce the default tcgen05 kernel — same MMAs, same accumulation order per accumulator —
-    for fprop (+bias, residual, ReLU) and dgrad; both are also held against fp64."""
-    torch.manual_seed(cin + cout)
-    k3, s3 = C._triple(k), C._triple(stride)
-    p3 = tuple(kk // 2 for kk in k3)
-    x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
-    w = torch.randn(cout, cin, *k3, device=DEV) / np.sqrt(cin * np.prod(k3))
-    b = torch.randn(cout, device=DEV)
-    os.environ.pop("MDT_TC_PAIR", None)
-    y0 = C.conv3d_forward(x, w, b, s3, p3, relu=True, algo=2)
-    gy = torch.randn_like(y0)
-    dx0 = C.conv3d_dgrad(gy, w, tuple(x.shape), s3, p3, algo=2)
-    try:
-        os.environ["MDT_TC_PAIR"] = "1"
-        y1 = C.conv3d_forward(x, w, b, s3, p3, relu=True, algo=2)
-        dx1 = C.conv3d_dgrad(gy, w, tuple(x.shape), s3, p3, algo=2)
-        torch.cuda.synchronize()
-    finally:
-        os.environ.pop("MDT_TC_PAIR", None)
-    assert _rel(y1, _ref(x, w, b, s3, p3, True, None)) < 1e-4
-    assert _rel(y1, y0.double()) < 2e-6 and _rel(dx1, dx0.double()) < 2e-6
