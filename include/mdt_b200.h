@@ -144,6 +144,12 @@ int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *desc_host, const void *x_sp
                               float *y, void *workspace, size_t workspace_bytes, void *stream);
 /* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
+/* which kernel family runs this descriptor/pass: 1 fp32 SIMT / direct stem, 2 tcgen05 halo-window implicit GEMM (conv3d_tc.cu, wgrad:
+ * conv3d_tc_wgrad.cu), 3 tcgen05 tap-stacked implicit GEMM (conv3d_tcw.cu: fprop/dgrad of lines of 65..128 voxels); 0 = unsupported */
+int mdt_conv3d_variant(const mdt_conv3d_desc *desc_host, int pass);
+/* diagnostics: cycle counters of CTA 0 of the tap-stacked kernel, accumulated while the environment has MDT_TCW_PROF=1 (16 values: producer
+ * wait-A / wait-B / total, MMA wait-A / wait-B / wait-accumulator / total, epilogue wait / total, tiles); synchronises the device and clears them */
+int mdt_debug_conv_tcw_prof(unsigned long long *out16_host);
 /* ------------------------------------------------------------- decoder up-sampling -----------------------------------------------------------
  * replaces: F.interpolate(x, scale_factor=(2,2,1), mode='trilinear', align_corners=False) of models/backbone.py:209-218 (P2/P1_upsample), NDHWC.
  * x [n, d, h, w, c] -> y [n, 2d, 2h, w, c]; c % 4 == 0; backward is the exact adjoint, written as a gather (no atomics, no zero fill). */

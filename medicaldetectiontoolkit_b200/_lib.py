@@ -55,6 +55,8 @@ SIGNATURES = {
     "mdt_conv3d_dgrad": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_conv3d_wgrad": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_conv3d_algo": (_I, [ctypes.POINTER(Conv3dDesc), _I]),
+    "mdt_conv3d_variant": (_I, [ctypes.POINTER(Conv3dDesc), _I]),
+    "mdt_debug_conv_tcw_prof": (_I, [ctypes.POINTER(ctypes.c_ulonglong)]),
     "mdt_conv3d_backward_fused": (_I, [ctypes.POINTER(Conv3dDesc), _I]),
     "mdt_conv3d_backward_workspace_bytes": (_SZ, [ctypes.POINTER(Conv3dDesc), _I]),
     "mdt_conv3d_backward": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -2,6 +2,7 @@
 #include "conv3d_common.cuh"
 
 namespace mdt {
+int conv_tcw_read_prof(unsigned long long *out16);
 // 1 = fp32 SIMT (generic implicit GEMM, or the direct stem kernels when Cin <= 4), 2 = tcgen05
 static int pick_algo(const mdt_conv3d_desc *c, const ConvGeom &g, int pass) {
     if (c->algo == 1) return 1;
@@ -21,6 +22,16 @@ int mdt_conv3d_algo(const mdt_conv3d_desc *c, int pass) {
     mdt::ConvGeom g;
     if (!mdt::make_geom(c, g) || pass < 0 || pass > 2) return MDT_EINVAL;
     return mdt::pick_algo(c, g, pass);
+}
+
+int mdt_debug_conv_tcw_prof(unsigned long long *out16) { return out16 ? mdt::conv_tcw_read_prof(out16) : MDT_EINVAL; }
+
+int mdt_conv3d_variant(const mdt_conv3d_desc *c, int pass) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || pass < 0 || pass > 2) return MDT_EINVAL;
+    const int algo = mdt::pick_algo(c, g, pass);
+    if (algo != 2) return algo;
+    return (pass < 2 && mdt::conv_tcw_supported(g, pass)) ? 3 : 2;
 }
 
 size_t mdt_conv3d_workspace_bytes(const mdt_conv3d_desc *c, int pass) {

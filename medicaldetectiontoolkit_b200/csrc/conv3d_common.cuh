@@ -34,8 +34,9 @@ bool conv_stem_supported(const ConvGeom &g, int pass);
 int conv_stem_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, float *y, int relu, cudaStream_t st);
 int conv_stem_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, cudaStream_t st);
 
-// tcgen05 (conv3d_tc.cu)
+// tcgen05 (conv3d_tc.cu; conv3d_tcw.cu for the tap-stacked variant)
 bool conv_tc_supported(const ConvGeom &g, int pass);
+bool conv_tcw_supported(const ConvGeom &g, int pass);
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
 int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
                   void *ws, size_t ws_bytes, cudaStream_t st);

@@ -375,13 +375,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-int conv_tc_kpad(int channels) { return channels <= 16 ? 16 : channels <= 32 ? 32 : ceil_div(channels, 64) * 64; }
+// channels of the canonical split layout in GLOBAL memory: padded to 16 only (36 -> 48).  Kernels that stage wider chunks in shared memory
+// (conv_tc_kpad_smem) let the TMA box run past the tensor's channel extent: out-of-bounds elements arrive as zeros.
+int conv_tc_kpad(int channels) { return ceil_div(channels, 16) * 16; }
+int conv_tc_kpad_smem(int channels) { return channels <= 16 ? 16 : channels <= 32 ? 32 : ceil_div(channels, 64) * 64; }
+
+bool conv_tcw_supported(const ConvGeom &g, int pass);
+size_t conv_tcw_workspace_bytes(const ConvGeom &g, int pass, int precision);
+int conv_tcw_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst, int relu,
+                 int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit, __nv_bfloat16 *out_split);
 
 bool conv_tc_wgrad_supported(const ConvGeom &g);
 size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision);
 
 bool conv_tc_supported(const ConvGeom &g, int pass) {
     if (pass == 2) return conv_tc_wgrad_supported(g);
+    if (conv_tcw_supported(g, pass)) return true;
     const TcPlan pl = make_plan(g, pass);
     int a, b, c, d;
     return pl.ok && plan_stages(pl, g.kw, 2, a, b, c, d) && tmap_encode_fn() != nullptr;
@@ -397,16 +406,20 @@ static int weight_reps(const TcPlan &pl, int T, int planes) {
 
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
     if (pass == 2) return conv_tc_wgrad_workspace_bytes(g, precision);
+    const size_t tcw = conv_tcw_workspace_bytes(g, pass, precision);
     const TcPlan pl = make_plan(g, pass);
-    if (!pl.ok) return 0;
+    if (!pl.ok) return tcw;
     const int planes = precision == 1 ? 1 : 2;
     const int T = g.kd * g.kh * g.kw;
-    return align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024) + align_up((size_t)weight_reps(pl, T, planes) * planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
+    const size_t old = align_up((size_t)planes * pl.src_rows * pl.Kg * 2, 1024) + align_up((size_t)weight_reps(pl, T, planes) * planes * T * pl.Np * pl.Kp * 2, 1024) + 2048;
+    return old > tcw ? old : tcw;
 }
 
 // presplit != nullptr: the A operand is already in split form (layout of split_rows_kernel with inter_w = SW) and `src` is ignored
 int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
                 int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit) {
+    if (conv_tcw_supported(g, pass))   // lines of 65..128 voxels: the tap-stacked kernel (conv3d_tcw.cu)
+        return conv_tcw_run(g, pass, src, w, bias, residual, dst, relu, precision, ws, ws_bytes, st, presplit, nullptr);
     const TcPlan pl = make_plan(g, pass);
     if (!pl.ok) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_workspace_bytes(g, pass, precision)) return MDT_EWORKSPACE;
@@ -415,13 +428,13 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     const bool dgrad = pass == 1;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     __nv_bfloat16 *xs = presplit ? const_cast<__nv_bfloat16 *>(presplit) : reinterpret_cast<__nv_bfloat16 *>(base);
-    __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)planes * pl.src_rows * pl.Kp * 2, 1024));
+    __nv_bfloat16 *wp = reinterpret_cast<__nv_bfloat16 *>(base + align_up((size_t)planes * pl.src_rows * pl.Kg * 2, 1024));
 
     {   // operand preparation
-        const long long total = pl.src_rows * (pl.Kp / 8);
+        const long long total = pl.src_rows * (pl.Kg / 8);
         long long blocks = ceil_div<long long>(total, 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
-        if (!presplit) split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kp, planes, pl.SW, nullptr, nullptr, nullptr);
+        if (!presplit) split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, xs, pl.src_rows, pl.Kc, pl.Kg, planes, pl.SW, nullptr, nullptr, nullptr);
         int rc = launch_status();
         if (rc) return rc;
         const long long wt = (long long)T * pl.Np * pl.Kp;
@@ -458,13 +471,14 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     if (const char *e = getenv("MDT_TC_Q")) { const int v = atoi(e); if (v >= 1 && v <= p.Q) p.Q = v; }
     p.wreps = weight_reps(pl, T, planes);
 
-    // tensor maps.  A: bf16 [N*SD][SH][plane][SW][Kp] (N and D merged: out-of-range d taps are skipped explicitly, never fetched);
+    // tensor maps.  A: bf16 [N*SD][SH][plane][SW][Kg] (N and D merged: out-of-range d taps are skipped explicitly, never fetched; channel
+    //               chunks past Kg are TMA zero fill);
     //               B: bf16 [T][plane][Np][Kp]
     CUtensorMap tmA, tmB;
     {
-        const uint64_t line = (uint64_t)pl.SW * pl.Kp * 2;
-        const uint64_t dims[5] = {(uint64_t)pl.Kp, (uint64_t)pl.SW, (uint64_t)planes, (uint64_t)pl.SH, (uint64_t)g.n * pl.SD};
-        const uint64_t strides[4] = {(uint64_t)pl.Kp * 2, line, line * planes, line * planes * pl.SH};
+        const uint64_t line = (uint64_t)pl.SW * pl.Kg * 2;
+        const uint64_t dims[5] = {(uint64_t)pl.Kg, (uint64_t)pl.SW, (uint64_t)planes, (uint64_t)pl.SH, (uint64_t)g.n * pl.SD};
+        const uint64_t strides[4] = {(uint64_t)pl.Kg * 2, line, line * planes, line * planes * pl.SH};
         const uint32_t box[5] = {(uint32_t)(pl.swz / 2), (uint32_t)(pl.halo ? rows_loaded : pl.BW), (uint32_t)(pl.halo ? planes : 1), (uint32_t)pl.BH, 1u};
         if (!encode_bf16_tmap(&tmA, xs, 5, dims, strides, box, pl.swz)) return MDT_EDRIVER;
         const uint64_t bdims[4] = {(uint64_t)pl.Kp, (uint64_t)pl.Np, (uint64_t)planes, (uint64_t)T};

@@ -36,7 +36,7 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 
 struct TcPlan {
     bool ok = false;
-    int Kc, Kp, Nc, Np, NT, n_tiles_n, swz, nchunks, BW, BH, halo, a_rows;
+    int Kc, Kp, Kg, Nc, Np, NT, n_tiles_n, swz, nchunks, BW, BH, halo, a_rows;   // Kp: K padding in shared memory; Kg: channels of the global split layout
     int RD, RH, RW, SD, SH, SW;  // row space / source space
     long long src_rows, dst_rows;
 };
@@ -51,7 +51,8 @@ static inline TcPlan make_plan(const ConvGeom &g, int pass) {
     pl.RD = dgrad ? g.d : g.od; pl.RH = dgrad ? g.h : g.oh; pl.RW = dgrad ? g.w : g.ow;
     pl.SD = dgrad ? g.od : g.d; pl.SH = dgrad ? g.oh : g.h; pl.SW = dgrad ? g.ow : g.w;
     // K padding: one swizzle-span chunk for <= 64 channels (few, large TMA boxes), 64-channel chunks above
-    pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;   // == conv_tc_kpad(); padding to 16 only was measured 24 % slower
+    pl.Kp = pl.Kc <= 16 ? 16 : pl.Kc <= 32 ? 32 : ceil_div(pl.Kc, 64) * 64;   // == conv_tc_kpad_smem(); padding to 16 only was measured 24 % slower
+    pl.Kg = ceil_div(pl.Kc, 16) * 16;                                          // == conv_tc_kpad()
     pl.Np = ceil_div(pl.Nc, 16) * 16;
     pl.NT = pl.Np <= 128 ? pl.Np : 128;
     pl.n_tiles_n = ceil_div(pl.Np, pl.NT);

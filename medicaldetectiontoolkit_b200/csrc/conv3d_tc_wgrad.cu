@@ -22,7 +22,8 @@ using namespace tc;
 
 __global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long rows, int C, int Cp, int planes, int inter_w,
                                   const float *__restrict__ relu_of, float *__restrict__ masked_out, float *__restrict__ colsum);
-int conv_tc_kpad(int channels);
+int conv_tc_kpad(int channels);        // channels of the global split layout (multiple of 16)
+int conv_tc_kpad_smem(int channels);   // channels staged in shared memory (TMA zero-fills past the global extent)
 int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst, int relu,
                 int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit);
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
@@ -244,13 +245,13 @@ static WgPlan make_wg_plan(const ConvGeom &g) {
     WgPlan w;
     if (g.sw != 1) return w;
     // x (N side): one chunk spans all of ci when ci <= 64, so that all kw taps of a pair fit one MMA
-    w.ci_p = conv_tc_kpad(g.cin);   // same padding rule as the fprop/dgrad operands: split planes are interchangeable between the passes
+    w.ci_p = conv_tc_kpad_smem(g.cin);
     w.chunkx = w.ci_p < 64 ? w.ci_p : 64;
     w.swx = w.chunkx * 2;
     w.nxc = w.ci_p / w.chunkx;
     if (g.kw * w.chunkx > 256) return w;
     // dy (M side)
-    w.co_p = conv_tc_kpad(g.cout);
+    w.co_p = conv_tc_kpad_smem(g.cout);
     w.swy = w.co_p >= 64 ? 128 : w.co_p * 2;
     w.chunky = w.swy / 2;
     w.mtrick = (2 * w.co_p <= 128) ? 1 : 0;
@@ -320,7 +321,7 @@ size_t conv_tc_wgrad_workspace_bytes(const ConvGeom &g, int precision) {
     const int planes = precision == 1 ? 1 : 2;
     const size_t rows_y = (size_t)g.n * g.od * g.oh * g.ow, rows_x = (size_t)g.n * g.d * g.h * g.w;
     const size_t partial = (size_t)wg_splits(g, w) * w.groups * w.mtiles * 128 * wg_slot_cols(g, w) * sizeof(float);
-    return wg_align(planes * rows_y * w.co_p * 2) + wg_align(planes * rows_x * w.ci_p * 2) + wg_align(partial) + 2048;
+    return wg_align(planes * rows_y * conv_tc_kpad(g.cout) * 2) + wg_align(planes * rows_x * conv_tc_kpad(g.cin) * 2) + wg_align(partial) + 2048;
 }
 
 // dy_presplit != nullptr: dy is already split (interleaved layout, conv_tc_kpad(cout) channels); then db must have been produced by the caller
@@ -334,8 +335,9 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     const long long rows_y = (long long)g.n * g.od * g.oh * g.ow, rows_x = (long long)g.n * g.d * g.h * g.w;
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     __nv_bfloat16 *ys = dy_presplit ? const_cast<__nv_bfloat16 *>(dy_presplit) : reinterpret_cast<__nv_bfloat16 *>(base);
+    const int co_g = conv_tc_kpad(g.cout), ci_g = conv_tc_kpad(g.cin);   // channel extents of the split planes in global memory
     __nv_bfloat16 *xs = x_presplit ? const_cast<__nv_bfloat16 *>(x_presplit)
-                                   : reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2));
+                                   : reinterpret_cast<__nv_bfloat16 *>(base + wg_align((size_t)planes * rows_y * co_g * 2));
     auto split = [&](const float *src, __nv_bfloat16 *dst, long long rows, int C, int Cp, int line_w) {
         long long blocks = ceil_div<long long>(rows * (Cp / 8), 256);
         if (blocks > (long long)num_sms() * 32) blocks = (long long)num_sms() * 32;
@@ -343,8 +345,8 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
         return launch_status();
     };
     int rc = MDT_OK;
-    if (!dy_presplit && (rc = split(dy, ys, rows_y, g.cout, w.co_p, g.ow))) return rc;
-    if (!x_presplit && (rc = split(x, xs, rows_x, g.cin, w.ci_p, g.w))) return rc;
+    if (!dy_presplit && (rc = split(dy, ys, rows_y, g.cout, co_g, g.ow))) return rc;
+    if (!x_presplit && (rc = split(x, xs, rows_x, g.cin, ci_g, g.w))) return rc;
 
     TcWgradParams p{};
     p.NB = g.n; p.OD = g.od; p.OH = g.oh; p.OW = g.ow; p.D = g.d; p.H = g.h; p.W = g.w;
@@ -369,18 +371,18 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     p.splits = wg_splits(g, w);
     p.mtiles = w.mtiles;
     p.slot_cols = wg_slot_cols(g, w);
-    p.partial = reinterpret_cast<float *>(base + wg_align((size_t)planes * rows_y * w.co_p * 2) + wg_align((size_t)planes * rows_x * w.ci_p * 2));
+    p.partial = reinterpret_cast<float *>(base + wg_align((size_t)planes * rows_y * co_g * 2) + wg_align((size_t)planes * rows_x * ci_g * 2));
 
     CUtensorMap tmY, tmX;
     {
-        const uint64_t yl = (uint64_t)g.ow * w.co_p * 2;   // one W line of one plane
-        const uint64_t dims[5] = {(uint64_t)w.co_p, (uint64_t)g.ow, (uint64_t)planes, (uint64_t)g.oh, (uint64_t)g.n * g.od};
-        const uint64_t str[4] = {(uint64_t)w.co_p * 2, yl, yl * planes, yl * planes * g.oh};
+        const uint64_t yl = (uint64_t)g.ow * co_g * 2;   // one W line of one plane
+        const uint64_t dims[5] = {(uint64_t)co_g, (uint64_t)g.ow, (uint64_t)planes, (uint64_t)g.oh, (uint64_t)g.n * g.od};
+        const uint64_t str[4] = {(uint64_t)co_g * 2, yl, yl * planes, yl * planes * g.oh};
         const uint32_t box[5] = {(uint32_t)w.chunky, (uint32_t)w.rows_y, 1u, 1u, 1u};
         if (!encode_bf16_tmap(&tmY, ys, 5, dims, str, box, w.swy)) return MDT_EDRIVER;
-        const uint64_t xl = (uint64_t)g.w * w.ci_p * 2;
-        const uint64_t xd[5] = {(uint64_t)w.ci_p, (uint64_t)g.w, (uint64_t)planes, (uint64_t)g.h, (uint64_t)g.n * g.d};
-        const uint64_t xs_[4] = {(uint64_t)w.ci_p * 2, xl, xl * planes, xl * planes * g.h};
+        const uint64_t xl = (uint64_t)g.w * ci_g * 2;
+        const uint64_t xd[5] = {(uint64_t)ci_g, (uint64_t)g.w, (uint64_t)planes, (uint64_t)g.h, (uint64_t)g.n * g.d};
+        const uint64_t xs_[4] = {(uint64_t)ci_g * 2, xl, xl * planes, xl * planes * g.h};
         const uint32_t xbox[5] = {(uint32_t)w.chunkx, (uint32_t)w.rows_x, 1u, 1u, 1u};
         if (!encode_bf16_tmap(&tmX, xs, 5, xd, xs_, xbox, w.swx)) return MDT_EDRIVER;
     }

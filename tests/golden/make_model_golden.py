@@ -244,6 +244,7 @@ def make_model(case):
             with torch.no_grad():
                 rl, rd, _, det, dm = net.forward(img)
             out["rpn_logits"], out["rpn_deltas"] = sub(np_(rl)), sub(np_(rd))
+            out["class_scores"] = np_(net.batch_mrcnn_class_scores)
             out["rpn_logits_shape"] = np.array(rl.shape)
             out["detection_masks"] = sub(np_(dm))
             out["detection_masks_shape"] = np.array(dm.shape)

@@ -57,15 +57,19 @@ def oracle_roi_align(dim):
         @staticmethod
         def forward(ctx, image, boxes, box_ind, crop):
             ctx.save_for_backward(boxes, box_ind)
+            ctx.in_shape = tuple(image.shape)
+            # the C side reads sizes [0 .. 1 + dim] only (crop_and_resize_gpu.c:17-24): trailing singleton axes (the channel-last GT masks of
+            # mrcnn.py:556-559 arrive as [n, 1, y, x, z, 1]) are part of the same contiguous memory
+            image = image.detach().contiguous().reshape(image.shape[:2 + dim])
             ctx.im_size = tuple(image.shape)
-            out = O.crop_and_resize_forward(image.detach().contiguous().numpy(), boxes.detach().numpy(), box_ind.detach().numpy(), crop)
+            out = O.crop_and_resize_forward(image.numpy(), boxes.detach().numpy(), box_ind.detach().numpy(), crop)
             return torch.from_numpy(out)
 
         @staticmethod
         def backward(ctx, g):
             boxes, box_ind = ctx.saved_tensors
             gi = O.crop_and_resize_backward(g.contiguous().numpy(), boxes.detach().numpy(), box_ind.detach().numpy(), ctx.im_size)
-            return torch.from_numpy(gi), None, None, None
+            return torch.from_numpy(gi).reshape(ctx.in_shape), None, None, None
 
     class CropAndResizeFunction(object):
         def __init__(self, *args):

@@ -30,6 +30,18 @@ SHAPES = [
     (36, 144, (7, 7, 3), 1, 0, (7, 7, 3)),     # mrcnn Classifier conv1 with ks = pool_size
     (144, 288, 3, 1, 1, (4, 4, 8)),            # deep encoder conv2
     (36, 2, 1, 1, 0, (8, 8, 16)),              # final_conv (seg logits)
+    # lines of 65..128 voxels: the tap-stacked tcgen05 kernel (conv3d_tcw.cu) for fprop / dgrad
+    (36, 36, 3, 1, 1, (5, 7, 128)),            # P0_conv2: odd line count (half-empty last tile), K = 48 as 32 + 16 channel chunks
+    (18, 18, 3, 1, 1, (3, 6, 128)),            # C0 second conv: 2 CTAs per SM
+    (18, 18, 7, (2, 2, 1), 3, (8, 12, 128)),   # C1 k7 s(2,2,1): 9 source lines per kd, 7 shifts, dgrad with line parity
+    (64, 54, 3, 1, 1, (3, 4, 128)),            # regressor conv_final: 3 unstacked MMAs per K step
+    (36, 36, 3, 1, 1, (4, 4, 96)),             # line shorter than the 128-row tile
+    (72, 72, 3, 1, 1, (3, 4, 128)),            # K = 80 as 64 + 16
+    (36, 96, 3, 1, 1, (2, 3, 128)),            # N tiling: 3 x 96 columns > 256 -> two tiles of 84 / 12 channels
+    (36, 36, 1, 1, 0, (4, 4, 128)),            # 1x1x1: no shifts
+    (18, 36, 3, (2, 2, 1), 1, (6, 8, 128)),    # strided k3
+    (36, 36, 3, 1, 0, (5, 6, 128)),            # valid conv: output lines of 126 voxels
+    (36, 18, 3, 1, 1, (3, 5, 72)),             # 18 output channels (float2 stores), 72-voxel lines
 ]
 
 
@@ -83,6 +95,17 @@ def test_conv3d_fprop_dgrad_wgrad(cin, cout, k, stride, pad, sp):
                 dw, db = C.conv3d_wgrad(x, gy, tuple(w.shape), s3, p3, True, precision=prec, algo=algo)
                 assert _rel(dw, wd.grad) < tol, ("wgrad", algo, prec)
                 assert _rel(db, gy.double().sum(dim=(0, 2, 3, 4))) < tol, ("bgrad", algo, prec)
+
+
+def test_tap_stacked_kernel_is_selected_for_long_lines():
+    """fprop / dgrad of the W = 128 layers (the bulk of cfg2's FLOPs) must run on conv3d_tcw.cu, short lines on conv3d_tc.cu"""
+    lib = L.load()
+    for cin, cout, k, stride, pad, sp, want in [(36, 36, 3, 1, 1, (128, 128, 128), 3), (18, 18, 7, (2, 2, 1), 3, (128, 128, 128), 3),
+                                                (64, 64, 3, 1, 1, (32, 32, 128), 3), (18, 18, 3, 1, 1, (128, 128, 128), 3),
+                                                (64, 64, 3, 1, 1, (16, 16, 64), 2), (144, 144, 3, 1, 1, (8, 8, 32), 2)]:
+        d = C._desc((2, cin) + sp, (cout, cin) + C._triple(k), C._triple(stride), C._triple(pad), False, 0, 0)
+        assert [lib.mdt_conv3d_variant(d, ps) for ps in (0, 1)] == [want, want], (cin, cout, k, sp)
+        assert lib.mdt_conv3d_variant(d, 2) == 2
 
 
 def test_tc_path_covers_the_hot_layers():

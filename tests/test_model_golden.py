@@ -290,6 +290,7 @@ def test_retina_models_vs_reference(case):
 
     RU.compute_class_loss, RU.compute_bbox_loss = rec_c, rec_b
     try:
+        np.random.seed(0)          # the generator seeds numpy the same way: replays the reference's np.random.choice sub-sampling of positives
         res = net.train_forward(batch)
     finally:
         RU.compute_class_loss, RU.compute_bbox_loss = orig_c, orig_b
@@ -303,7 +304,8 @@ def test_retina_models_vs_reference(case):
     assert abs(float(res['torch_loss']) - float(g["loss"][0])) <= 1e-4 * abs(float(g["loss"][0]))
     assert [len(b) for b in res['boxes']] == g["n_boxes"].tolist()
     assert sorted(set(bx['box_type'] for b in res['boxes'] for bx in b)) == list(g["box_types"])
-    assert float(np.asarray(res['seg_preds']).sum()) == float(g["seg_preds_sum"][0])
+    # argmax of the seg logits: voxels whose two logits agree to ~1e-6 may fall on either side
+    assert abs(float(np.asarray(res['seg_preds']).sum()) - float(g["seg_preds_sum"][0])) <= 1e-4 * np.asarray(res['seg_preds']).size
     _check_grads(net, g, model, 2e-3)
 
 
@@ -343,9 +345,13 @@ def test_mrcnn_vs_reference(case):
             return out
         return f
 
+    # second-stage class scores of all proposals (what SHEM ranks the negatives by)
+    if close.all():
+        assert _rel(_np(net.batch_mrcnn_class_scores), g["class_scores"]) <= 1e-4
     for n in names:
         setattr(MR, n, rec(n))
     try:
+        np.random.seed(0)
         res = net.train_forward(batch)
     finally:
         for n in names:
