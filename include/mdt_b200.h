@@ -142,6 +142,11 @@ size_t mdt_conv3d_split_bytes(const mdt_conv3d_desc *desc_host);
 int mdt_conv3d_split(const mdt_conv3d_desc *desc_host, const float *x, void *x_split, void *stream);
 int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *desc_host, const void *x_split, const float *w, const float *bias, const float *residual,
                               float *y, void *workspace, size_t workspace_bytes, void *stream);
+/* mdt_conv3d_fprop_presplit that ALSO emits the result y in canonical split form (mdt_conv3d_out_split_bytes bytes; layout of mdt_conv3d_split
+ * applied to y, padding channels zero) from the conv epilogue: the consumer conv then needs no split pass over y (tcgen05 path only). */
+size_t mdt_conv3d_out_split_bytes(const mdt_conv3d_desc *desc_host);
+int mdt_conv3d_fprop_presplit_out(const mdt_conv3d_desc *desc_host, const void *x_split, const float *w, const float *bias, const float *residual,
+                                  float *y, void *y_split, void *workspace, size_t workspace_bytes, void *stream);
 /* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
 /* which kernel family runs this descriptor/pass: 1 fp32 SIMT / direct stem, 2 tcgen05 halo-window implicit GEMM (conv3d_tc.cu, wgrad:

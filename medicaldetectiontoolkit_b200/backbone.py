@@ -9,7 +9,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .conv import Conv3d, Conv2d, _Conv3dFn
+from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
 
 _CL3 = torch.channels_last_3d
 
@@ -22,7 +22,7 @@ def _fused_residual_relu(conv_mod, x, residual):
     """relu(conv(x) + bias + residual) in one kernel when conv_mod is a bare libmdt conv; generic fallback otherwise"""
     if isinstance(conv_mod, Conv3d):
         return _Conv3dFn.apply(x, conv_mod.weight, conv_mod.bias, _to_cl(residual), conv_mod.stride, conv_mod.padding, True, conv_mod.precision,
-                               conv_mod.algo)
+                               conv_mod.algo, conv_mod.emit_split)
     if isinstance(conv_mod, Conv2d):
         y = _Conv3dFn.apply(x.unsqueeze(2), conv_mod.weight.unsqueeze(2), conv_mod.bias, residual.unsqueeze(2), (1,) + conv_mod.stride,
                             (0,) + conv_mod.padding, True, conv_mod.precision, conv_mod.algo)
@@ -144,7 +144,7 @@ class FPN(nn.Module):
         self.P4_conv1 = conv(sf * 16, oc, ks=1, stride=1, relu=None)
         self.P3_conv1 = conv(sf * 8, oc, ks=1, stride=1, relu=None)
         self.P2_conv1 = conv(sf * 4, oc, ks=1, stride=1, relu=None)
-        self.P1_conv1 = conv(sf, oc, ks=1, stride=1, relu=None)
+        self.P1_conv1 = no_split_consumer(conv(sf, oc, ks=1, stride=1, relu=None))   # p1_pre only feeds the (2,2,1) up-sampling
         if operate_stride1:
             self.P0_conv1 = conv(sf, oc, ks=1, stride=1, relu=None)
             self.P0_conv2 = conv(oc, oc, ks=3, stride=1, pad=1, relu=None)
@@ -162,7 +162,7 @@ class FPN(nn.Module):
         """conv(c) + other with the add fused into the conv epilogue when conv_mod is a bare libmdt conv"""
         if isinstance(conv_mod, Conv3d):
             return _Conv3dFn.apply(c, conv_mod.weight, conv_mod.bias, _to_cl(other), conv_mod.stride, conv_mod.padding, False, conv_mod.precision,
-                                   conv_mod.algo)
+                                   conv_mod.algo, conv_mod.emit_split)
         return conv_mod(c) + other
 
     @staticmethod
@@ -172,7 +172,7 @@ class FPN(nn.Module):
         fused = None
         if isinstance(conv_mod, Conv3d):
             fused = _Conv3dFn.apply(c, conv_mod.weight, conv_mod.bias, _to_cl(up), conv_mod.stride, conv_mod.padding, False, conv_mod.precision,
-                                    conv_mod.algo)
+                                    conv_mod.algo, conv_mod.emit_split)
         return fused if fused is not None else conv_mod(c) + up
 
     def forward(self, x):

@@ -24,6 +24,9 @@ DEFAULT_ALGO = 0
 
 _ws_cache = {}
 
+# conv modules whose output feeds another conv emit the bf16 split planes of their result from the epilogue (module attribute emit_split)
+EMIT_SPLIT = True
+
 # when a list, every conv kernel call appends a (start, end) CUDA-event pair recorded on the launching stream (bench.py roofline)
 EVENT_LOG = None
 
@@ -103,9 +106,11 @@ def _split_of(lib, x, d, precision):
     return xs
 
 
-def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, precision=None, algo=None, want_split=False):
+def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, precision=None, algo=None, want_split=False, emit_split=False):
     """y = relu?(conv3d(x, weight) + bias (+ residual)); x logical [N, C, D, H, W]; returns a channels_last_3d tensor. No autograd.
-    want_split: also return the split form of x used by the tcgen05 path (or None) so the caller can hand it to the backward pass."""
+    want_split: also return the split form of x used by the tcgen05 path (or None) so the caller can hand it to the backward pass.
+    emit_split: on the tcgen05 path the conv epilogue also writes y as (hi, lo) bf16 planes (mdt_conv3d_fprop_presplit_out) and caches them
+    on y, so that a conv consuming y skips its operand-split pass (split_rows_kernel was 8 % of the round-1 step)."""
     lib = L.load()
     L.require_cuda(x, weight, bias, residual)
     precision = DEFAULT_PRECISION if precision is None else precision
@@ -122,7 +127,13 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
     xs = None
     if which == 2:
         xs = _split_of(lib, x, d, precision)
-        L.check(lib.mdt_conv3d_fprop_presplit(d, L.ptr(xs), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        if emit_split and EMIT_SPLIT:
+            ys = torch.empty(lib.mdt_conv3d_out_split_bytes(d), dtype=torch.uint8, device=x.device)
+            L.check(lib.mdt_conv3d_fprop_presplit_out(d, L.ptr(xs), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ys), L.ptr(ws), ws.numel(),
+                                                      L.stream_ptr()))
+            y._mdt_split = (ys, y._version, precision)
+        else:
+            L.check(lib.mdt_conv3d_fprop_presplit(d, L.ptr(xs), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
     else:
         L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
     _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), which))
@@ -197,9 +208,9 @@ def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, 
 
 class _Conv3dFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, stride, padding, relu, precision, algo):
+    def forward(ctx, x, weight, bias, residual, stride, padding, relu, precision, algo, emit_split=False):
         prec = DEFAULT_PRECISION if precision is None else precision
-        y, xs = conv3d_forward(x, weight, bias, stride, padding, relu, residual, prec, algo, want_split=True)
+        y, xs = conv3d_forward(x, weight, bias, stride, padding, relu, residual, prec, algo, want_split=True, emit_split=emit_split)
         ctx.cfg = (stride, padding, relu, prec, algo, tuple(x.shape), bias is not None, residual is not None)
         ctx.xs = xs   # split form of x: the weight gradient reads it instead of splitting x again
         ctx.save_for_backward(x, weight, y if relu else None)
@@ -218,7 +229,7 @@ class _Conv3dFn(torch.autograd.Function):
             if fused is not None:
                 gx, gw, gb, gm = fused
                 gres = (gm if relu else gy) if (has_res and ctx.needs_input_grad[3]) else None
-                return gx, gw, gb, gres, None, None, None, None, None
+                return gx, gw, gb, gres, None, None, None, None, None, None
         if relu:
             gy = torch.ops.aten.threshold_backward(gy, y, 0.0)  # ReLU mask (elementwise, HBM-bound)
         gx = gw = gb = None
@@ -227,7 +238,7 @@ class _Conv3dFn(torch.autograd.Function):
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             gw, gb = conv3d_wgrad(x, gy, tuple(weight.shape), stride, padding, has_bias, precision, algo)
         gres = gy if (has_res and ctx.needs_input_grad[3]) else None
-        return gx, gw, gb, gres, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None
 
 
 def _triple(v):
@@ -248,6 +259,7 @@ class Conv3d(nn.Module):
         self.fused_relu = fused_relu
         self.precision = None
         self.algo = None
+        self.emit_split = True      # set False on convs whose output never feeds another conv (final layers, laterals feeding adds)
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *self.kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
         self.reset_parameters()
@@ -261,7 +273,7 @@ class Conv3d(nn.Module):
             nn.init.uniform_(self.bias, -bound, bound)
 
     def forward(self, x, residual=None):
-        return _Conv3dFn.apply(x, self.weight, self.bias, residual, self.stride, self.padding, self.fused_relu, self.precision, self.algo)
+        return _Conv3dFn.apply(x, self.weight, self.bias, residual, self.stride, self.padding, self.fused_relu, self.precision, self.algo, self.emit_split)
 
     def extra_repr(self):
         return "{}, {}, kernel_size={}, stride={}, padding={}, fused_relu={}".format(
@@ -278,6 +290,7 @@ class Conv2d(nn.Module):
         self.fused_relu = fused_relu
         self.precision = None
         self.algo = None
+        self.emit_split = False     # the split cache is keyed on the 5-D tensor; 2-D convs re-wrap their activations (unsqueeze) per call
         self.weight = nn.Parameter(torch.empty(out_channels, in_channels, *self.kernel_size))
         self.bias = nn.Parameter(torch.empty(out_channels)) if bias else None
         nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -290,6 +303,15 @@ class Conv2d(nn.Module):
         y = _Conv3dFn.apply(x.unsqueeze(2), self.weight.unsqueeze(2), self.bias, res, (1,) + self.stride, (0,) + self.padding,
                             self.fused_relu, self.precision, self.algo)
         return y.squeeze(2)
+
+
+def no_split_consumer(module):
+    """mark the conv inside an NDConvGenerator result (bare conv or Sequential) as NOT feeding another conv: its epilogue then skips the
+    bf16 split planes of the result (final layers of heads, laterals that only feed adds / up-sampling)"""
+    for m in module.modules():
+        if isinstance(m, (Conv3d, Conv2d)):
+            m.emit_split = False
+    return module
 
 
 class FusedReLU(nn.Module):

@@ -111,6 +111,21 @@ int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *c, const void *x_split, con
     return mdt::conv_tc_fprop_presplit(g, x_split, w, bias, residual, y, c->relu, c->precision, ws, ws_bytes, mdt::as_stream(stream));
 }
 
+int mdt_conv3d_fprop_presplit_out(const mdt_conv3d_desc *c, const void *x_split, const float *w, const float *bias, const float *residual, float *y,
+                                  void *y_split, void *ws, size_t ws_bytes, void *stream) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g) || !x_split || !w || !y || !y_split) return MDT_EINVAL;
+    if (mdt::pick_algo(c, g, 0) != 2) return MDT_EUNSUPPORTED;
+    if (ws_bytes < mdt_conv3d_workspace_bytes(c, 0) || !ws) return MDT_EWORKSPACE;
+    return mdt::conv_tc_fprop_presplit(g, x_split, w, bias, residual, y, c->relu, c->precision, ws, ws_bytes, mdt::as_stream(stream), y_split);
+}
+
+size_t mdt_conv3d_out_split_bytes(const mdt_conv3d_desc *c) {
+    mdt::ConvGeom g;
+    if (!mdt::make_geom(c, g)) return 0;
+    return mdt::conv_tc_split_bytes((long long)g.n * g.od * g.oh * g.ow, g.cout, c->precision);
+}
+
 int mdt_conv3d_backward(const mdt_conv3d_desc *c, const float *x, const void *x_split, const float *dy, const float *y_relu, const float *w,
                         float *dx, float *dw, float *db, float *dy_masked_out, void *ws, size_t ws_bytes, void *stream) {
     mdt::ConvGeom g;

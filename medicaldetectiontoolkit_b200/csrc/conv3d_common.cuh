@@ -52,6 +52,6 @@ int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const f
 size_t conv_tc_split_bytes(long long rows, int channels, int precision);
 int conv_tc_split(const float *x, long long rows, int channels, int line_w, int precision, void *out, cudaStream_t st);
 int conv_tc_fprop_presplit(const ConvGeom &g, const void *x_split, const float *w, const float *bias, const float *residual, float *y, int relu,
-                           int precision, void *ws, size_t ws_bytes, cudaStream_t st);
+                           int precision, void *ws, size_t ws_bytes, cudaStream_t st, void *y_split = nullptr);
 
 }  // namespace mdt

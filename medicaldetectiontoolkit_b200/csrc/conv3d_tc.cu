@@ -201,7 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // =============================================================== TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t ph = 1;   // parity to wait for on `empty` (fresh barrier: the "previous" phase counts as complete)
                     for (int kd = 0; kd < p.KD; ++kd)
@@ -240,7 +240,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // =============================================================== MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc1 = make_idesc_bf16(128, p.NT, 0, 0);
             const uint32_t idesc2 = make_idesc_bf16(128, 2 * p.NT, 0, 0);
             // descriptor template: everything but the start address (low 14 bits of the low word)
@@ -345,26 +345,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
                 const int col = n0 + c0 + j;
-                if (col >= p.Cn) break;
+                if (col >= p.Cn && !(p.out_split && col < p.out_kg)) break;
                 float o[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = v[j + k] + s_bias[c0 + j + k];
-                if (vec4) {
-                    if (p.residual) {
-                        const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + row_off + col));
-                        o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                if (col < p.Cn) {
+                    if (vec4) {
+                        if (p.residual) {
+                            const float4 rr = __ldg(reinterpret_cast<const float4 *>(p.residual + row_off + col));
+                            o[0] += rr.x; o[1] += rr.y; o[2] += rr.z; o[3] += rr.w;
+                        }
+                        if (p.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+                        *reinterpret_cast<float4 *>(p.out + row_off + col) = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (col + k >= p.Cn) break;
+                            float x = o[k];
+                            if (p.residual) x += __ldg(p.residual + row_off + col + k);
+                            if (p.relu) x = fmaxf(x, 0.f);
+                            p.out[row_off + col + k] = x;
+                            o[k] = x;
+                        }
                     }
-                    if (p.relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
-                    *reinterpret_cast<float4 *>(p.out + row_off + col) = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
+                }
+                if (p.out_split && col < p.out_kg) {
+                    // the same values as (hi, lo) bf16 planes for the next conv: [line][plane][w][out_kg]; channels >= Cn are written as zeros
+                    __align__(8) __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (col + k >= p.Cn) break;
-                        float x = o[k];
-                        if (p.residual) x += __ldg(p.residual + row_off + col + k);
-                        if (p.relu) x = fmaxf(x, 0.f);
-                        p.out[row_off + col + k] = x;
+                        const float x = (col + k < p.Cn) ? o[k] : 0.f;
+                        hi[k] = __float2bfloat16_rn(x);
+                        lo[k] = __float2bfloat16_rn(x - __bfloat162float(hi[k]));
                     }
+                    const size_t line = ((size_t)nb * p.RD + rd) * p.RH + rh;
+                    const size_t so = ((line * p.planes) * (size_t)p.RW + rw) * (size_t)p.out_kg + col;
+                    *reinterpret_cast<uint2 *>(p.out_split + so) = *reinterpret_cast<const uint2 *>(hi);
+                    if (p.planes > 1) *reinterpret_cast<uint2 *>(p.out_split + so + (size_t)p.RW * p.out_kg) = *reinterpret_cast<const uint2 *>(lo);
                 }
             }
         }
@@ -417,9 +434,9 @@ size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision) {
 
 // presplit != nullptr: the A operand is already in split form (layout of split_rows_kernel with inter_w = SW) and `src` is ignored
 int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst,
-                int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit) {
-    if (conv_tcw_supported(g, pass))   // lines of 65..128 voxels: the tap-stacked kernel (conv3d_tcw.cu)
-        return conv_tcw_run(g, pass, src, w, bias, residual, dst, relu, precision, ws, ws_bytes, st, presplit, nullptr);
+                int relu, int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit, __nv_bfloat16 *out_split) {
+    if (conv_tcw_supported(g, pass))   // the tap-stacked kernel (conv3d_tcw.cu) where it wins
+        return conv_tcw_run(g, pass, src, w, bias, residual, dst, relu, precision, ws, ws_bytes, st, presplit, out_split);
     const TcPlan pl = make_plan(g, pass);
     if (!pl.ok) return MDT_EUNSUPPORTED;
     if (ws_bytes < conv_tc_workspace_bytes(g, pass, precision)) return MDT_EWORKSPACE;
@@ -458,6 +475,7 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
     p.b_chunk_bytes = (int)align_up((size_t)p.TPS * planes * p.b_plane_bytes, 1024);
     p.a_region_bytes = p.CPS * p.a_chunk_bytes;
     p.relu = relu; p.bias = bias; p.residual = residual; p.out = dst;
+    p.out_split = out_split; p.out_kg = conv_tc_kpad(pl.Nc);
     // Accumulator chains.  For speed one chain is enough (the accumulate dependency is not the limiter), but the tensor core's fp32 accumulation
     // truncates: the error of a TMEM accumulator grows ~1e-7 of the result per chained MMA (tools/wgrad_precision.py).  3x3x3 layers chain
     // <= 216 MMAs (2e-5); the 7x7x7 stem conv would chain 1372, so its MMAs rotate over Q accumulators that the epilogue adds in IEEE fp32.
@@ -498,14 +516,15 @@ int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, c
 
 int conv_tc_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
                   void *ws, size_t ws_bytes, cudaStream_t st) {
-    return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st, nullptr);
+    return conv_tc_run(g, 0, x, w, bias, residual, y, relu, precision, ws, ws_bytes, st, nullptr, nullptr);
 }
 int conv_tc_fprop_presplit(const ConvGeom &g, const void *x_split, const float *w, const float *bias, const float *residual, float *y, int relu,
-                           int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
-    return conv_tc_run(g, 0, nullptr, w, bias, residual, y, relu, precision, ws, ws_bytes, st, reinterpret_cast<const __nv_bfloat16 *>(x_split));
+                           int precision, void *ws, size_t ws_bytes, cudaStream_t st, void *y_split) {
+    return conv_tc_run(g, 0, nullptr, w, bias, residual, y, relu, precision, ws, ws_bytes, st, reinterpret_cast<const __nv_bfloat16 *>(x_split),
+                       reinterpret_cast<__nv_bfloat16 *>(y_split));
 }
 int conv_tc_dgrad(const ConvGeom &g, const float *dy, const float *w, float *dx, int precision, void *ws, size_t ws_bytes, cudaStream_t st) {
-    return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st, nullptr);
+    return conv_tc_run(g, 1, dy, w, nullptr, nullptr, dx, 0, precision, ws, ws_bytes, st, nullptr, nullptr);
 }
 
 }  // namespace mdt

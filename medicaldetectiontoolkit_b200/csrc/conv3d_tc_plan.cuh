@@ -26,6 +26,8 @@ struct TcConvParams {
     int wreps;            // weight replicas in global memory
     const float *bias, *residual;
     float *out;
+    __nv_bfloat16 *out_split;   // optional: the result also as (hi, lo) bf16 planes in the canonical split layout [line][plane][w][out_kg]
+    int out_kg;
 };
 
 constexpr int kTcThreads = 192;

@@ -25,7 +25,7 @@ __global__ void split_rows_kernel(const float *__restrict__ src, __nv_bfloat16 *
 int conv_tc_kpad(int channels);        // channels of the global split layout (multiple of 16)
 int conv_tc_kpad_smem(int channels);   // channels staged in shared memory (TMA zero-fills past the global extent)
 int conv_tc_run(const ConvGeom &g, int pass, const float *src, const float *w, const float *bias, const float *residual, float *dst, int relu,
-                int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit);
+                int precision, void *ws, size_t ws_bytes, cudaStream_t st, const __nv_bfloat16 *presplit, __nv_bfloat16 *out_split);
 size_t conv_tc_workspace_bytes(const ConvGeom &g, int pass, int precision);
 
 struct TcWgradParams {
@@ -93,7 +93,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     };
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             for (long long u = split; u < p.units; u += p.splits, ++it) {
                 int n, od, oh, ow0;
@@ -127,7 +127,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, ncols, 1, 1);
             const uint32_t lty = layout_type_for_swizzle_bytes(p.swy), ltx = layout_type_for_swizzle_bytes(p.swx);
             // descriptor templates (everything but the 14-bit start address); the x descriptor's LBO is ONE ROW: next N chunk = next kw shift
@@ -447,7 +447,7 @@ int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const f
     split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, ys, rows_y, g.cout, co_p, planes, g.ow, relu_of, dy_masked_out, db);
     int rc = launch_status();
     if (rc) return rc;
-    if (dx && (rc = conv_tc_run(g, 1, nullptr, w, nullptr, nullptr, dx, 0, precision, inner, inner_bytes, st, ys))) return rc;
+    if (dx && (rc = conv_tc_run(g, 1, nullptr, w, nullptr, nullptr, dx, 0, precision, inner, inner_bytes, st, ys, nullptr))) return rc;
     return conv_tc_wgrad_impl(g, x, nullptr, dw, nullptr, precision, inner, inner_bytes, st, ys, reinterpret_cast<const __nv_bfloat16 *>(x_split));
 }
 

@@ -42,6 +42,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// one lane of a converged warp (elect.sync): inside `if (elect_one())` the compiler knows exactly one lane runs, so the uniform-register
+// operands of tcgen05.mma / TMA instructions are set with plain R2UR moves.  Under `if (lane == 0)` every such instruction was wrapped in an
+// ELECT + 5 x R2UR.BROADCAST + branch "waterfall" (~60 cycles each, seen in the SASS; tools/mma_pipe_probe.cu measures 48-64 cycles per
+// back-to-back MMA without it).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 from . import model_utils as mutils
 from . import native_ops
 from .backbone import FPN
-from .conv import Conv3d, NDConvGenerator, _Conv3dFn
+from .conv import Conv3d, NDConvGenerator, _Conv3dFn, no_split_consumer
 from .native_ops import CropAndResizeFunction as ra3D, CropAndResizeFunction2D as ra2D
 from .retina_unet import compute_bbox_loss as _pos_bbox_loss, compute_class_loss as _shem_class_loss
 
@@ -33,8 +33,8 @@ class RPN(nn.Module):
         super().__init__()
         self.dim = conv.dim
         self.conv_shared = conv(cf.end_filts, cf.n_rpn_features, ks=3, stride=cf.rpn_anchor_stride, pad=1, relu=cf.relu)
-        self.conv_class = conv(cf.n_rpn_features, 2 * len(cf.rpn_anchor_ratios), ks=1, stride=1, relu=None)
-        self.conv_bbox = conv(cf.n_rpn_features, 2 * self.dim * len(cf.rpn_anchor_ratios), ks=1, stride=1, relu=None)
+        self.conv_class = no_split_consumer(conv(cf.n_rpn_features, 2 * len(cf.rpn_anchor_ratios), ks=1, stride=1, relu=None))
+        self.conv_bbox = no_split_consumer(conv(cf.n_rpn_features, 2 * self.dim * len(cf.rpn_anchor_ratios), ks=1, stride=1, relu=None))
 
     def forward(self, x):
         x = self.conv_shared(x)
@@ -56,7 +56,7 @@ class Classifier(nn.Module):
         self.pyramid_levels = cf.pyramid_levels
         norm = cf.norm if cf.norm != 'instance_norm' else None
         self.conv1 = conv(cf.end_filts, cf.end_filts * 4, ks=self.pool_size, stride=1, norm=norm, relu=cf.relu)
-        self.conv2 = conv(cf.end_filts * 4, cf.end_filts * 4, ks=1, stride=1, norm=norm, relu=cf.relu)
+        self.conv2 = no_split_consumer(conv(cf.end_filts * 4, cf.end_filts * 4, ks=1, stride=1, norm=norm, relu=cf.relu))
         self.linear_class = nn.Linear(cf.end_filts * 4, cf.head_classes)
         self.linear_bbox = nn.Linear(cf.end_filts * 4, cf.head_classes * 2 * self.dim)
 
@@ -109,7 +109,7 @@ class Mask(nn.Module):
         self.conv4 = conv(cf.end_filts, cf.end_filts, ks=3, stride=1, pad=1, norm=cf.norm, relu=cf.relu)
         self.deconv = _Deconv2x(cf.end_filts, cf.end_filts, conv.dim)
         self.relu = nn.ReLU(inplace=True) if cf.relu == 'relu' else nn.LeakyReLU(inplace=True)
-        self.conv5 = conv(cf.end_filts, cf.head_classes, ks=1, stride=1, relu=None)
+        self.conv5 = no_split_consumer(conv(cf.end_filts, cf.head_classes, ks=1, stride=1, relu=None))
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x, rois):
@@ -443,6 +443,7 @@ class net(nn.Module):
         max_pos = max(1, cf.rpn_train_anchors_per_image // 2)
         rpn_class_loss = img.new_zeros(1)
         rpn_bbox_loss = img.new_zeros(1)
+        monitor = []
         for b in range(n_b):
             if len(gt_boxes[b]) > 0:
                 for ix in range(len(gt_boxes[b])):
@@ -451,10 +452,23 @@ class net(nn.Module):
             else:
                 rpn_match = torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device)
                 rpn_target_deltas = torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device)
-            cl, _ = compute_rpn_class_loss(rpn_match, rpn_class_logits[b], cf.shem_poolsize, max_pos=max_pos)
+            cl, neg_ix = compute_rpn_class_loss(rpn_match, rpn_class_logits[b], cf.shem_poolsize, max_pos=max_pos)
+            monitor.append((rpn_match, neg_ix))
             rpn_class_loss = rpn_class_loss + cl / n_b
             rpn_bbox_loss = rpn_bbox_loss + compute_rpn_bbox_loss(rpn_target_deltas, rpn_pred_deltas[b], rpn_match, max_pos=max_pos) / n_b
         if kwargs.get('monitor_anchors', True):
+            # positive / sampled-negative anchors of the RPN loss for the monitoring plots (mrcnn.py:896-916)
+            sp = img.shape[2:]
+            hi = np.array([sp[0], sp[1], sp[0], sp[1]] + ([sp[2], sp[2]] if cf.dim == 3 else []))
+            for b, (match, neg_ix) in enumerate(monitor):
+                m = match.cpu().numpy()
+                neg_all = np.where(m == -1)[0]
+                nix = neg_ix.cpu().numpy()
+                for p_ in np.clip(self.np_anchors[m == 1], 0, hi):
+                    box_results_list[b].append({'box_coords': p_, 'box_type': 'pos_anchor'})
+                if neg_all.size:
+                    for n_ in np.clip(self.np_anchors[neg_all[nix[nix >= 0]]], 0, hi):
+                        box_results_list[b].append({'box_coords': n_, 'box_type': 'neg_anchor'})
             props = proposal_boxes.cpu().numpy()
             for b in range(n_b):
                 for r in props[b][props[b][:, -1].argsort()][::-1][:cf.n_plot_rpn_props, :-1]:

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from . import model_utils as mutils
 from . import native_ops
 from .backbone import FPN
-from .conv import NDConvGenerator
+from .conv import NDConvGenerator, no_split_consumer
 
 _CL3 = torch.channels_last_3d
 
@@ -36,7 +36,7 @@ class _Tower(nn.Module):
         self.conv_2 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
         self.conv_3 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
         self.conv_4 = conv(n_feat, n_feat, ks=3, stride=s, pad=1, relu=cf.relu)
-        self.conv_final = conv(n_feat, cf.n_anchors_per_pos * out_per_anchor, ks=3, stride=s, pad=1, relu=None)
+        self.conv_final = no_split_consumer(conv(n_feat, cf.n_anchors_per_pos * out_per_anchor, ks=3, stride=s, pad=1, relu=None))
 
     def forward(self, x):
         y = self.conv_final(self.conv_4(self.conv_3(self.conv_2(self.conv_1(x)))))
@@ -225,7 +225,7 @@ class net(nn.Module):
         self.Classifier = Classifier(cf, conv)
         self.BBRegressor = BBRegressor(cf, conv)
         if self.has_seg_head:
-            self.final_conv = conv(cf.end_filts, cf.num_seg_classes, ks=1, pad=0, norm=None, relu=None)
+            self.final_conv = no_split_consumer(conv(cf.end_filts, cf.num_seg_classes, ks=1, pad=0, norm=None, relu=None))
 
     # -------------------------------------------------------------------------------------------------------------- forward
     def forward(self, img):

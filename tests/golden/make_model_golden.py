@@ -186,7 +186,7 @@ def make_model(case):
         rcf.operate_stride1 = cf.operate_stride1
         net = m.net(rcf, RS.Logger())
         GI.tame_(detweights.fill_(net), model)
-        batch = GI.synthetic_batch(cf, B, seed=5, with_masks=(model == 'mrcnn'))
+        batch = GI.synthetic_batch(cf, B, seed=GI.case_seed(case), with_masks=(model == 'mrcnn'))
         img = T(batch['data']).float()
 
         if model == 'mrcnn':
@@ -245,6 +245,14 @@ def make_model(case):
                 rl, rd, _, det, dm = net.forward(img)
             out["rpn_logits"], out["rpn_deltas"] = sub(np_(rl)), sub(np_(rd))
             out["class_scores"] = np_(net.batch_mrcnn_class_scores)
+            # margin of the SHEM picks: lowest selected negative vs best unselected negative of the same element (printed; want >> 1e-4)
+            fg = out["class_scores"][:, 1:].max(1)
+            P_ = fg.shape[0] // B
+            neg_ix = out["dtl_ix"][out["dtl_cls"] == 0]
+            for b in range(B):
+                sel = neg_ix[(neg_ix >= b * P_) & (neg_ix < (b + 1) * P_)]
+                rest = np.setdiff1d(np.arange(b * P_, (b + 1) * P_), out["dtl_ix"])
+                print("    shem margin elem", b, float(fg[sel].min() - np.sort(fg[rest])[-1]), "sel", sel)
             out["rpn_logits_shape"] = np.array(rl.shape)
             out["detection_masks"] = sub(np_(dm))
             out["detection_masks_shape"] = np.array(dm.shape)

@@ -98,13 +98,15 @@ def test_conv3d_fprop_dgrad_wgrad(cin, cout, k, stride, pad, sp):
 
 
 def test_tap_stacked_kernel_is_selected_for_long_lines():
-    """fprop / dgrad of the W = 128 layers (the bulk of cfg2's FLOPs) must run on conv3d_tcw.cu, short lines on conv3d_tc.cu"""
+    """fprop / dgrad of the long-line layers with few K steps and >= 112 stacked columns (36 -> 36/64 k3, 18 -> 18 k7: where it measured
+    faster, profiles/r02_tcw_layers.txt) run on conv3d_tcw.cu, the others on conv3d_tc.cu"""
     lib = L.load()
-    for cin, cout, k, stride, pad, sp, want in [(36, 36, 3, 1, 1, (128, 128, 128), 3), (18, 18, 7, (2, 2, 1), 3, (128, 128, 128), 3),
-                                                (64, 64, 3, 1, 1, (32, 32, 128), 3), (18, 18, 3, 1, 1, (128, 128, 128), 3),
-                                                (64, 64, 3, 1, 1, (16, 16, 64), 2), (144, 144, 3, 1, 1, (8, 8, 32), 2)]:
+    for cin, cout, k, stride, pad, sp, want in [(36, 36, 3, 1, 1, (128, 128, 128), [3, 3]), (18, 18, 7, (2, 2, 1), 3, (128, 128, 128), [3, 3]),
+                                                (36, 64, 3, 1, 1, (32, 32, 128), [3, 2]), (64, 64, 3, 1, 1, (32, 32, 128), [2, 2]),
+                                                (18, 18, 3, 1, 1, (128, 128, 128), [2, 2]), (64, 64, 3, 1, 1, (16, 16, 64), [2, 2]),
+                                                (144, 144, 3, 1, 1, (8, 8, 32), [2, 2])]:
         d = C._desc((2, cin) + sp, (cout, cin) + C._triple(k), C._triple(stride), C._triple(pad), False, 0, 0)
-        assert [lib.mdt_conv3d_variant(d, ps) for ps in (0, 1)] == [want, want], (cin, cout, k, sp)
+        assert [lib.mdt_conv3d_variant(d, ps) for ps in (0, 1)] == want, (cin, cout, k, sp)
         assert lib.mdt_conv3d_variant(d, 2) == 2
 
 
@@ -175,3 +177,31 @@ def test_fused_backward_relu_residual_bias(cin, cout, sp):
         assert _rel(x.grad, xd.grad) < TOL
     d = C._desc(tuple(x.shape), tuple(w.shape), (1, 1, 1), (pad,) * 3, False, 0, 0)
     assert L.load().mdt_conv3d_backward_fused(d, int(cin > 1)) == (1 if cin > 4 else 0)    # fused tcgen05 path; the Cin<=4 stem uses the direct kernels
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,sp", [(36, 36, 3, 1, (3, 5, 128)), (36, 64, 3, 1, (2, 4, 128)), (64, 64, 3, 1, (2, 4, 128)), (64, 54, 3, 1, (4, 8, 32)),
+                                                    (18, 18, 7, (2, 2, 1), (8, 8, 128)), (72, 18, 1, 1, (4, 4, 32)), (18, 72, 1, 1, (3, 4, 128))])
+def test_epilogue_emits_the_split_planes_of_the_result(cin, cout, k, stride, sp):
+    """mdt_conv3d_fprop_presplit_out: the (hi, lo) bf16 planes written by the conv epilogue are byte-identical to mdt_conv3d_split applied to
+    the fp32 result (incl. zero padding channels), for both tcgen05 fprop kernels; a consumer conv fed from them gives identical output"""
+    torch.manual_seed(cin * 7 + cout)
+    lib = L.load()
+    k3, s3 = C._triple(k), C._triple(stride)
+    p3 = tuple(kk // 2 for kk in k3)
+    x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randn(cout, cin, *k3, device=DEV) / np.sqrt(cin * np.prod(k3))
+    b = torch.randn(cout, device=DEV)
+    d = C._desc(tuple(x.shape), tuple(w.shape), s3, p3, True, 0, 0)
+    if lib.mdt_conv3d_algo(d, 0) != 2:
+        pytest.skip("shape not on the tcgen05 path")
+    y0 = C.conv3d_forward(x, w, b, s3, p3, relu=True)
+    y1 = C.conv3d_forward(x, w, b, s3, p3, relu=True, emit_split=True)
+    assert torch.equal(y0, y1)
+    ys, ver, prec = y1._mdt_split
+    w2 = torch.randn(8, cout, 1, 1, 1, device=DEV)
+    d2 = C._desc(tuple(y1.shape), tuple(w2.shape), (1, 1, 1), (0, 0, 0), False, 0, 0)
+    want = torch.empty(lib.mdt_conv3d_split_bytes(d2), dtype=torch.uint8, device=DEV)
+    assert want.numel() == ys.numel()
+    L.check(lib.mdt_conv3d_split(d2, L.ptr(y0), L.ptr(want), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(ys, want), (int((ys != want).sum()), ys.numel())

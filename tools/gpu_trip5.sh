@@ -1,0 +1,14 @@
+#!/usr/bin/env bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_conv_gpu.py -q --tb=short -x 2>&1 | tail -30 > gpurun_out/conv_gpu.txt
+tail -4 gpurun_out/conv_gpu.txt
+timeout 300 python tools/tcw_prof.py p0_36 c0_18 c1_k7 head64 bb54 > gpurun_out/tcw_prof.txt 2>&1
+PASS=1 timeout 300 python tools/tcw_prof.py p0_36 c1_k7 head64 >> gpurun_out/tcw_prof.txt 2>&1
+echo "== STACK=1" >> gpurun_out/tcw_prof.txt
+MDT_TCW_STACK=1 timeout 300 python tools/tcw_prof.py p0_36 >> gpurun_out/tcw_prof.txt 2>&1
+echo "== STACK=0" >> gpurun_out/tcw_prof.txt
+MDT_TCW_STACK=0 timeout 300 python tools/tcw_prof.py c0_18 >> gpurun_out/tcw_prof.txt 2>&1
+cat gpurun_out/tcw_prof.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tcw_kernel -c 1 -o gpurun_out/ncu_tcw_p0_v3 python tools/tcw_prof.py p0_36 --once > gpurun_out/ncu_tcw.log 2>&1
+timeout 600 python -m pytest tests/test_model_golden.py -m gpu -q --tb=short 2>&1 > gpurun_out/golden_gpu.txt
+tail -12 gpurun_out/golden_gpu.txt
