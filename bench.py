@@ -70,6 +70,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
 def run_reference(args):
     """CPU arm: the port of the step on the host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -83,53 +93,72 @@ def run_reference(args):
     torch.set_num_threads(cores)
     patch = tuple(args.patch)
     cf = make_cf('retina_unet', 3, patch)
-    # bounded sample: one step of `b` patches; drop to batch 1 if a step is slow, so that K+W steps end within a few minutes
+    # same config as the GPU arm: batch, warm-up and step count as requested; only if W + K steps would exceed the time box (a CPU step of
+    # 2 x 128^3 patches takes ~14 s) the number of TIMED steps shrinks — never the batch or the warm-up
     b = args.batch
     batch = synthetic_batch(cf, b, seed=0)
-    t0 = time.perf_counter()
     t_first, used = cpu_step.time_cpu_steps(cf, batch, steps=1, warmup=0, threads=cores)
-    budget = 240.0
-    total_steps = args.steps + args.warmup
-    if t_first[0] * total_steps > budget and b > 1:
-        b = 1
-        batch = synthetic_batch(cf, b, seed=0)
-    steps = max(1, min(args.steps, int(budget / max(t_first[0] * b / args.batch, 1e-3)) - args.warmup))
-    times, used = cpu_step.time_cpu_steps(cf, batch, steps=steps, warmup=min(args.warmup, 1), threads=cores)
+    budget = float(os.environ.get("MDT_REF_BUDGET_S", "540"))
+    warm = args.warmup
+    steps = max(1, min(args.steps, int(budget / max(t_first[0], 1e-3)) - warm - 1))
+    times, used = cpu_step.time_cpu_steps(cf, batch, steps=steps, warmup=max(warm - 1, 0), threads=cores)   # the probe step above was warm-up 1
     ms = 1e3 * sum(times) / len(times)
     val = b / (ms / 1e3)
     sample = "%d full train step(s) of %d patch(es) %s (forward+detections+matching+losses+backward+Adam), fp32, torch CPU" % (len(times), b, "x".join(map(str, patch)))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "patches/s", "n_gpus": args.gpus, "steps": len(times),
-            "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "configs[1]: lidc_exp 3D Retina U-Net, synthetic 1-ch %s patches, batch %d per GPU" % ("x".join(map(str, patch)), args.batch),
                        "global_batch": b, "parallelism": "host cores (%d threads)" % used, "optimizer": "Adam lr 1e-4",
                        "sample": "each step = one full train step of %d patch(es) on the CPU" % b},
-            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": used, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "patches/s", "cores": used, "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "kind": "port",
+                             "sample": sample},
             "e2e": {"value": val, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def make_roofline(step_flops, conv_ms, n_conv_calls, ms_step, dom, peak_tf, peaks_measured):
+def load_traffic(shape):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of THIS round (profiles/r02_traffic.json, written from
+    `ncu --set full`: dram__bytes_read.sum + dram__bytes_write.sum), or None when there is no capture for this shape"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        for e in t.get("entries", []):
+            if tuple(e["input_shape"]) == tuple(shape):
+                return e
+    except Exception:
+        pass
+    return None
+
+
+def make_roofline(step_flops, conv_ms, n_conv_calls, ms_step, dom, peak_tf, peaks_measured, slowest=None, traffic=None):
     """roofline object of the JSON line.  Top level = the dominant kernel launch (the heaviest forward conv: flops of that launch / its
-    CUDA-event duration measured live in the timed region, DRAM traffic from its ncu capture); `all_conv_launches` = the same ratio over
-    every conv call of the step.  dom = (flops, ms, tag, calls_per_step) or None; pure function (tests/test_bench_cpu.py)."""
+    CUDA-event duration measured live in a separate instrumented pass, DRAM traffic from its committed ncu capture); `slowest_launch` = the conv
+    call with the longest average duration (a fused backward: dy split + dgrad + wgrad); `all_conv_launches` = the same ratio over every
+    conv call of the step.  dom / slowest = (flops, ms, tag, calls_per_step) or None; pure function (tests/test_bench_cpu.py)."""
     if not conv_ms:
         return None
     src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks_measured else "fallback 1.4 PF sustained (of fallback)"
     ach = step_flops / (conv_ms / 1e3) / 1e12
     agg = {"kernel": "conv3d fprop+dgrad+wgrad (all layers, %d launches/step)" % round(n_conv_calls), "achieved": ach, "unit": "TFLOP/s",
            "frac": ach / peak_tf, "algorithmic_flops_per_step": step_flops, "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_step}
+
+    def describe(tag):
+        names = ("fprop", "dgrad", "wgrad", "fused backward (dy split + dgrad + wgrad)")
+        return "%s %d->%d k%s on %s" % (names[tag[0]], tag[1][1], tag[2][0], "x".join(map(str, tag[2][2:])), "x".join(map(str, tag[1])))
     if dom is None:
         roof = {"bound": "tensor", "kernel": agg["kernel"], "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None}
     else:
         fl, ms_k, tag, _ = dom
-        roof = {"bound": "tensor",
-                "kernel": "conv_tc_kernel fprop %d->%d k%s on %s (incl. its operand split/pack launches)" % (tag[1][1], tag[2][0], "x".join(map(str, tag[2][2:])), "x".join(map(str, tag[1]))),
+        roof = {"bound": "tensor", "kernel": "conv " + describe(tag) + " (kernel + its weight pack launch; operand planes come from the producer's epilogue)",
                 "achieved": fl / ms_k / 1e9, "peak": peak_tf, "unit": "TFLOP/s", "frac": fl / ms_k / 1e9 / peak_tf,
-                "traffic": 1.655e9 if tuple(tag[1]) == (2, 36, 128, 128, 128) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this launch (profiles/r01_ncu_ops_summary.txt, conv_tc_kernel 36->36: 1.074 GB + 0.584 GB; algorithmic minimum 4*(in+out) = 1.21 GB)",
+                "traffic": traffic["dram_bytes"] if traffic else None,
+                "traffic_source": traffic["source"] if traffic else None,
                 "algorithmic_flops": fl, "ms": ms_k,
                 "note": "fp32-faithful split-bf16 arithmetic issues 3 bf16 MMAs per algorithmic MAC: at most 1/3 of the bf16 peak by construction"}
+    if slowest is not None:
+        fl, ms_k, tag, n = slowest
+        roof["slowest_launch"] = {"kernel": "conv " + describe(tag), "ms": ms_k, "algorithmic_flops": fl, "achieved": fl / ms_k / 1e9, "unit": "TFLOP/s",
+                                  "frac": fl / ms_k / 1e9 / peak_tf, "calls_per_step": n}
     roof["peak_source"] = src
     roof["all_conv_launches"] = agg
     return roof
@@ -146,6 +175,8 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 = fp32-faithful conv (default, parity mode); 1 = single-pass bf16")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 force SIMT conv, 2 force tcgen05 conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="retina_unet", choices=["retina_unet", "mrcnn"],
+                    help="retina_unet = BASELINE configs[1] (the metric's config); mrcnn = configs[2]: 3D Mask R-CNN, 512 proposals, RoIAlign 7x7x3")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -155,7 +186,7 @@ def main():
     import torch.distributed as dist
     from medicaldetectiontoolkit_b200 import _lib as L
     from medicaldetectiontoolkit_b200 import conv as C
-    from medicaldetectiontoolkit_b200 import retina_unet
+    from medicaldetectiontoolkit_b200 import mrcnn, retina_unet
     from medicaldetectiontoolkit_b200.configs import make_cf, synthetic_batch
     from medicaldetectiontoolkit_b200.parallel import FlatGradAllReduce
 
@@ -175,14 +206,18 @@ def main():
     C.DEFAULT_ALGO = args.algo
 
     patch = tuple(args.patch)
-    cf = make_cf('retina_unet', 3, patch, batch_size=args.batch)
+    cf = make_cf(args.model, 3, patch, batch_size=args.batch)
+    is_mrcnn = args.model == 'mrcnn'
+    if is_mrcnn:   # BASELINE configs[2]: 512 proposals per element, one second-stage chunk
+        cf.post_nms_rois_training = cf.post_nms_rois_inference = 512
+        cf.roi_chunk_size = 1024
     torch.manual_seed(0)          # identical replicas on every rank
     np.random.seed(1000 + rank)   # disjoint data streams / sub-sampling streams
-    net = retina_unet.net(cf, None).to(dev)
+    net = (mrcnn if is_mrcnn else retina_unet).net(cf, None).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=cf.learning_rate[0], weight_decay=cf.weight_decay, fused=True)
     reducer = FlatGradAllReduce(net, world)
 
-    host_batches = [synthetic_batch(cf, args.batch, seed=100 * rank + i) for i in range(2)]
+    host_batches = [synthetic_batch(cf, args.batch, seed=100 * rank + i, with_masks=is_mrcnn) for i in range(2)]
     for hb in host_batches:  # pinned host staging, as a loader would provide
         hb['data'] = torch.from_numpy(hb['data']).pin_memory()
         hb['seg'] = torch.from_numpy(hb['seg']).pin_memory()
@@ -232,31 +267,39 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # --- kernel-resident throughput (inputs already in HBM) with conv-kernel time measured live by CUDA events on the launching stream
-    C.EVENT_LOG = [] if rank == 0 else None
+    # --- kernel-resident throughput (inputs already in HBM), uninstrumented
     launches0 = lib.mdt_launch_count()
     torch.cuda.profiler.start()     # no-op unless run under `ncu --profile-from-start off`: the launch list then covers exactly the timed steps
     ms_dev = timed(dev_batches, args.steps)
     torch.cuda.profiler.stop()
     launches = lib.mdt_launch_count() - launches0
+    # --- separate instrumented pass: every conv call bracketed by CUDA events on the launching stream (roofline object only)
     conv_ms = None
-    if C.EVENT_LOG is not None:
+    if rank == 0:
+        n_inst = min(args.steps, 4)
+        C.EVENT_LOG = []
+        for i in range(n_inst):
+            step(dev_batches[i % 2])
         torch.cuda.synchronize()
-        conv_ms = sum(a.elapsed_time(b) for a, b, _ in C.EVENT_LOG) / args.steps
-        n_conv_calls = len(C.EVENT_LOG) / args.steps
-        # the single heaviest launch: forward conv of the largest-FLOP layer (P0_conv2 36->36 k3 at full resolution for the 128^3 config)
+        log, C.EVENT_LOG = C.EVENT_LOG, None
+        conv_ms = sum(a.elapsed_time(b) for a, b, _ in log) / n_inst
+        n_conv_calls = len(log) / n_inst
         per_tag = {}
-        for a, b, tag in C.EVENT_LOG:
-            if tag is not None and tag[0] == 0:
+        for a, b, tag in log:
+            if tag is not None:
                 per_tag.setdefault(tag, []).append(a.elapsed_time(b))
-        dom = None
+        dom = slowest = None
         for tag, ts in per_tag.items():
-            _, xs, ws, st, which = tag
-            fl = 2.0 * xs[0] * (xs[2] // st[0]) * (xs[3] // st[1]) * (xs[4] // st[2]) * ws[0] * ws[1] * ws[2] * ws[3] * ws[4]
-            calls_per_step = len(ts) / args.steps
-            if dom is None or fl > dom[0]:
-                dom = (fl, sum(ts) / len(ts), tag, calls_per_step)
-    C.EVENT_LOG = None
+            ps, xs, ws, st, which = tag
+            fl = 2.0 * xs[0] * (xs[2] // st[0]) * (xs[3] // st[1]) * (xs[4] // st[2]) * ws[0] * ws[1] * ws[2] * ws[3] * ws[4] * (2.0 if ps == 3 else 1.0)
+            ent = (fl, sum(ts) / len(ts), tag, len(ts) / n_inst)
+            if ps == 0 and (dom is None or fl > dom[0]):      # the single heaviest forward launch (P0_conv2 36->36 k3 at full resolution for cfg2)
+                dom = ent
+            if slowest is None or ent[1] > slowest[1]:
+                slowest = ent
+    elif world > 1:
+        for i in range(min(args.steps, 4)):                   # keep the ranks in step (the all-reduce is collective)
+            step(dev_batches[i % 2])
     # --- end to end through the public API with host buffers
     ms_e2e = timed(host_batches, args.steps)
     if rank == 0:
@@ -277,26 +320,35 @@ def main():
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     step_flops = 3.0 * fwd_flops
-    roof = make_roofline(step_flops, conv_ms, n_conv_calls if conv_ms else 0, ms_dev / args.steps, dom if conv_ms else None, peak_tf, bool(peaks))
+    traffic = load_traffic(dom[2][1]) if (conv_ms and dom) else None
+    roof = make_roofline(step_flops, conv_ms, n_conv_calls if conv_ms else 0, ms_dev / args.steps, dom if conv_ms else None, peak_tf, bool(peaks),
+                         slowest if conv_ms else None, traffic)
     h2d = sum(int(hb['data'].numel() * hb['data'].element_size() + hb['seg'].numel() * hb['seg'].element_size()) for hb in host_batches[:1])
+    if is_mrcnn:
+        h2d = int(host_batches[0]['data'].numel() * 4 + sum(int(np.asarray(m).size) for m in host_batches[0]['roi_masks']))   # image + GT masks (uint8)
     d2h = int(args.batch * np.prod(patch)) + 60 * 9 * 4 + 5 * 4  # seg_preds uint8 + detections + loss scalars
-    line = {"metric": METRIC, "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    if is_mrcnn:
+        d2h = 60 * 9 * 4 + 6 * 4 + args.batch * 512 * 7 * 4       # detections + loss scalars + proposals for the monitoring boxes
+    workload = ("configs[1]: lidc_exp 3D Retina U-Net, synthetic 1-ch %s patches, batch %d per GPU" if not is_mrcnn else
+                "configs[2]: lidc_exp 3D Mask R-CNN (mrcnn.py), %s patches, 512 proposals, RoIAlign 7x7x3, batch %d per GPU") % ("x".join(map(str, patch)), args.batch)
+    line = {"metric": METRIC if not is_mrcnn else "patches_per_sec_128cubed_mask_rcnn_train_step", "value": value, "unit": "patches/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (conv: split-bf16 x3 on tcgen05, fp32 accumulate)" if args.precision == 0 else "bf16",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: lidc_exp 3D Retina U-Net, synthetic 1-ch %s patches, batch %d per GPU" % ("x".join(map(str, patch)), args.batch),
+            "config": {"workload": workload,
                        "global_batch": args.batch * world, "parallelism": "dp%d" % world, "optimizer": "Adam lr 1e-4",
                        "l2": "no flush needed: per-step activation working set (>5 GB) far exceeds the 126 MB L2",
                        "conv_precision": args.precision, "conv_algo": args.algo},
             "e2e": {"value": e2e, "unit": "patches/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof}
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not is_mrcnn:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import cpu_step
         cores = cpu_step.calibrate_threads(os.cpu_count() or 1)
         cb = synthetic_batch(cf, args.batch, seed=0)
         times, used = cpu_step.time_cpu_steps(cf, cb, steps=1, warmup=0, threads=cores)
-        line["cpu_baseline"] = {"value": args.batch / times[0], "unit": "patches/s", "cores": used, "kind": "port",
+        line["cpu_baseline"] = {"value": args.batch / times[0], "unit": "patches/s", "cores": used, "host_cpus": os.cpu_count(), "cpu_model": cpu_model(),
+                                "kind": "port",
                                 "sample": "1 full train step of %d patches %s on the host cores (oracle/cpu_step.py: torch CPU fp32 convs, numpy fp64 matching, C NMS)" % (args.batch, "x".join(map(str, patch)))}
     print(json.dumps(line))
     if world > 1:

@@ -9,7 +9,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
+try:
+    from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
+except ImportError:   # loaded by FILE PATH as the reference does (utils.import_module('bbone', cf.backbone_path), mrcnn.py:842): no parent package
+    from medicaldetectiontoolkit_b200.conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
 
 _CL3 = torch.channels_last_3d
 

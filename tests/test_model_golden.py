@@ -393,3 +393,24 @@ def test_mrcnn_vs_reference(case):
     assert abs(float(res['torch_loss']) - float(g["loss"][0])) <= 2e-4 * abs(float(g["loss"][0]))
     assert sorted(set(bx['box_type'] for b in res['boxes'] for bx in b)) == list(g["box_types"])
     _check_grads(net, g, model, 1e-2)
+
+
+# ================================================================================================== CPU: the bench's CPU port is pinned too
+def test_cpu_port_matches_reference_goldens():
+    """oracle/cpu_step.py (the `--impl reference` / cpu_baseline arm: stock torch.nn.Conv3d on the host) reproduces the logits of the
+    reference's own models/retina_unet.py under the same weights — the timed CPU arm computes the reference's function"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_step
+    case = "retina_unet_small"
+    g = np.load(os.path.join(GOLD, "model_%s.npz" % case))
+    cf, model, B = GI.model_case(case)
+    net = cpu_step.build_cpu_net(cf)
+    assert [k for k, _ in net.named_parameters()] == list(g["keys"])
+    GI.tame_(detweights.fill_(net), model)
+    img = T(GI.synthetic_batch(cf, B, seed=GI.case_seed(case))['data'])
+    with torch.no_grad():
+        cl, bb, seg = net(img)
+    assert list(cl.shape) == g["class_logits_shape"].tolist()
+    assert _rel(sub(_np(cl)), g["class_logits"]) <= 1e-4
+    assert _rel(sub(_np(bb)), g["bb_outputs"]) <= 1e-4
+    assert _rel(sub(_np(seg)), g["seg_logits"]) <= 1e-4
