@@ -79,6 +79,19 @@ int mdt_crop_and_resize_2d_backward(const float *grads, const int64_t *grad_stri
                                     int batch, int image_height, int image_width, int crop_height, int crop_width, int depth,
                                     float *grads_image, const int64_t *img_strides_host, int zero_init, int64_t image_numel, void *stream);
 
+/* pyramid RoIAlign: ONE launch over all FPN levels.  replaces: models/mrcnn.py:373-457 pyramid_roi_align's per-level loop (boolean-mask gather,
+ * up to 4 CropAndResize calls, concat, un-permute through a sort).  roi_level[n] in [0, nlevels) selects the map of RoI n (the reference's
+ * round(4 + log2(sqrt(h*w))) rule is evaluated by the caller); every crop row is written exactly once, bad box_ind rows are zeros.
+ * images / grad_images: HOST arrays of nlevels device pointers (channels-last maps, C % 4 == 0); image_strides: nlevels x 5 int64 element strides
+ * (b, c, y, x, z); image_dims: nlevels x 3 (H, W, Z).  Returns MDT_EUNSUPPORTED for layouts outside the vector kernel (caller then loops over
+ * levels with mdt_crop_and_resize_*).  dim = 2 or 3 (2: crop_zdepth and the Z entries are ignored). */
+int mdt_pyramid_roi_align_forward(int dim, const float *const *images, const int64_t *image_strides, const int *image_dims, int nlevels, const float *boxes,
+                                  const int *box_ind, const int *roi_level, int num_boxes, int batch, int crop_height, int crop_width, int crop_zdepth,
+                                  int depth, float *crops, const int64_t *crop_strides, void *stream);
+int mdt_pyramid_roi_align_backward(int dim, const float *grads, const int64_t *grad_strides, const float *boxes, const int *box_ind, const int *roi_level,
+                                   int num_boxes, int batch, int crop_height, int crop_width, int crop_zdepth, int depth, float *const *grad_images,
+                                   const int64_t *image_strides, const int *image_dims, int nlevels, int zero_init, const int64_t *image_numel, void *stream);
+
 /* ------------------------------------------------------------ anchor <-> GT matching --------------------------------------------------------
  * replaces: utils/model_utils.py:505-619 gt_anchor_matching (+ compute_overlaps :83-110, compute_iou_{2D,3D} :35-79), which runs in numpy f64 on the host.
  * anchors [A, 2*dim] f64, gt_boxes [G, 2*dim] f64, gt_class_ids [G] int32 (NULL => all 1, the RPN case of mrcnn.py:894).

@@ -47,6 +47,9 @@ SIGNATURES = {
     "mdt_crop_and_resize_3d_backward": (_I, [_VP, c_i64p, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP, c_i64p, _I, _I64, _VP]),
     "mdt_crop_and_resize_2d_forward": (_I, [_VP, c_i64p, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP, c_i64p, _VP]),
     "mdt_crop_and_resize_2d_backward": (_I, [_VP, c_i64p, _VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP, c_i64p, _I, _I64, _VP]),
+    "mdt_pyramid_roi_align_forward": (_I, [_I, ctypes.POINTER(_VP), c_i64p, ctypes.POINTER(_I), _I, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP, c_i64p, _VP]),
+    "mdt_pyramid_roi_align_backward": (_I, [_I, _VP, c_i64p, _VP, _VP, _VP, _I, _I, _I, _I, _I, _I, ctypes.POINTER(_VP), c_i64p, ctypes.POINTER(_I), _I, _I,
+                                            c_i64p, _VP]),
     "mdt_anchor_match_workspace_bytes": (_SZ, [_I]),
     "mdt_anchor_match": (_I, [_I, _VP, _I, _VP, _VP, _I, _D, _D, _VP, _SZ, _VP, _VP, _VP, _VP]),
     "mdt_anchor_delta_targets": (_I, [_I, _VP, _VP, _VP, _VP, _I, _I, ctypes.POINTER(_D), _VP, _VP]),

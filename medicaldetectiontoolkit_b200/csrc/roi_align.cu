@@ -215,9 +215,8 @@ struct RoiTables {
 };
 
 template <int DIM, bool BWD>
-__global__ void __launch_bounds__(kRoiThreads) roi_cl4_per_roi(RoiGeom g, const float *__restrict__ src, const float *__restrict__ boxes,
-                                                              const int *__restrict__ box_ind, float *__restrict__ dst, int bins_per_slice) {
-    __shared__ RoiTables s;
+__device__ __forceinline__ void roi_cl4_per_roi_body(const RoiGeom &g, const float *__restrict__ src, const float *__restrict__ boxes,
+                                                     const int *__restrict__ box_ind, float *__restrict__ dst, int bins_per_slice, RoiTables &s) {
     const int n = blockIdx.x, tid = threadIdx.x;
     const int P = g.ch * g.cw * g.cz;
     const int bin0 = blockIdx.y * bins_per_slice, nbins = min(P - bin0, bins_per_slice);
@@ -302,6 +301,41 @@ __global__ void __launch_bounds__(kRoiThreads) roi_cl4_per_roi(RoiGeom g, const 
         bl += dq; c4 += dr;
         if (c4 >= C4) { c4 -= C4; ++bl; }
     }
+}
+
+template <int DIM, bool BWD>
+__global__ void __launch_bounds__(kRoiThreads) roi_cl4_per_roi(RoiGeom g, const float *__restrict__ src, const float *__restrict__ boxes,
+                                                              const int *__restrict__ box_ind, float *__restrict__ dst, int bins_per_slice) {
+    __shared__ RoiTables s;
+    roi_cl4_per_roi_body<DIM, BWD>(g, src, boxes, box_ind, dst, bins_per_slice, s);
+}
+
+// ---- pyramid variant: ONE launch for all levels of an FPN (replaces the per-level loop of models/mrcnn.py:405-447 — boolean-mask gather,
+// <= 4 crop_and_resize calls, concat, un-permute by sort).  Every RoI carries its level; its CTA reads that level's map geometry, so each
+// output row is written exactly once and, in the backward pass, each level's gradient map receives only its own RoIs.
+constexpr int kMaxPyrLevels = 5;
+struct PyrGeom {
+    int num_boxes, batch, ch, cw, cz, C, nlevels;
+    int64_t os[5];
+    int H[kMaxPyrLevels], W[kMaxPyrLevels], Z[kMaxPyrLevels];
+    int64_t is[kMaxPyrLevels][5];
+    float *map[kMaxPyrLevels];        // forward: source maps (read only); backward: gradient maps
+};
+
+template <int DIM, bool BWD>
+__global__ void __launch_bounds__(kRoiThreads) roi_cl4_pyramid(const __grid_constant__ PyrGeom pg, const float *__restrict__ crops_or_grads,
+                                                              const float *__restrict__ boxes, const int *__restrict__ box_ind,
+                                                              const int *__restrict__ roi_level, float *__restrict__ crops_out, int bins_per_slice) {
+    __shared__ RoiTables s;
+    int lv = roi_level[blockIdx.x];
+    lv = lv < 0 ? 0 : (lv >= pg.nlevels ? pg.nlevels - 1 : lv);
+    RoiGeom g;
+    g.num_boxes = pg.num_boxes; g.batch = pg.batch; g.H = pg.H[lv]; g.W = pg.W[lv]; g.Z = pg.Z[lv];
+    g.ch = pg.ch; g.cw = pg.cw; g.cz = pg.cz; g.C = pg.C;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { g.is[k] = pg.is[lv][k]; g.os[k] = pg.os[k]; }
+    if (!BWD) roi_cl4_per_roi_body<DIM, false>(g, pg.map[lv], boxes, box_ind, crops_out, bins_per_slice, s);
+    else      roi_cl4_per_roi_body<DIM, true>(g, crops_or_grads, boxes, box_ind, pg.map[lv], bins_per_slice, s);
 }
 
 // the per-RoI kernels keep tap offsets in 32 bits, tap tables of 64 entries per axis and <= 256 channel groups
@@ -393,9 +427,63 @@ static int roi_backward(const float *grads, const int64_t *gs, const float *boxe
     return launch_status();
 }
 
+template <int DIM>
+static int pyramid_run(bool bwd, float *const *maps, const int64_t *is, const int *dims, int nlevels, const float *crops_or_grads, const float *boxes,
+                       const int *box_ind, const int *roi_level, int num_boxes, int batch, int ch, int cw, int cz, int C, float *crops_out,
+                       const int64_t *os, int zero_init, const int64_t *numel, cudaStream_t st) {
+    if (nlevels <= 0 || nlevels > kMaxPyrLevels || num_boxes < 0 || batch <= 0 || ch <= 0 || cw <= 0 || cz <= 0 || C <= 0 || !maps || !is || !dims || !os)
+        return MDT_EINVAL;
+    PyrGeom pg{};
+    pg.num_boxes = num_boxes; pg.batch = batch; pg.ch = ch; pg.cw = cw; pg.cz = cz; pg.C = C; pg.nlevels = nlevels;
+    for (int k = 0; k < DIM + 2; ++k) pg.os[k] = os[k];
+    const float *crop_ptr = bwd ? crops_or_grads : crops_out;
+    for (int l = 0; l < nlevels; ++l) {
+        pg.H[l] = dims[3 * l]; pg.W[l] = dims[3 * l + 1]; pg.Z[l] = DIM == 3 ? dims[3 * l + 2] : 1;
+        for (int k = 0; k < DIM + 2; ++k) pg.is[l][k] = is[5 * l + k];
+        pg.map[l] = maps[l];
+        if (!maps[l] || pg.H[l] <= 0 || pg.W[l] <= 0 || pg.Z[l] <= 0) return MDT_EINVAL;
+        RoiGeom g{num_boxes, batch, pg.H[l], pg.W[l], pg.Z[l], ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+        for (int k = 0; k < 5; ++k) { g.is[k] = pg.is[l][k]; g.os[k] = pg.os[k]; }
+        if (!cl4_ok(g, maps[l], crop_ptr) || !per_roi_ok(g)) return MDT_EUNSUPPORTED;   // caller falls back to one launch per level
+        if (bwd && zero_init) {
+            if (!numel || numel[l] <= 0) return MDT_EINVAL;
+            cudaError_t e = cudaMemsetAsync(maps[l], 0, (size_t)numel[l] * sizeof(float), st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (num_boxes == 0) return MDT_OK;
+    if (!boxes || !box_ind || !roi_level || !crop_ptr) return MDT_EINVAL;
+    RoiGeom g0{num_boxes, batch, pg.H[0], pg.W[0], pg.Z[0], ch, cw, cz, C, {0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    dim3 grid; int bins;
+    per_roi_grid(g0, grid, bins);
+    if (!bwd) roi_cl4_pyramid<DIM, false><<<grid, kRoiThreads, 0, st>>>(pg, nullptr, boxes, box_ind, roi_level, crops_out, bins);
+    else      roi_cl4_pyramid<DIM, true><<<grid, kRoiThreads, 0, st>>>(pg, crops_or_grads, boxes, box_ind, roi_level, nullptr, bins);
+    return launch_status();
+}
+
 }  // namespace mdt
 
 extern "C" {
+
+int mdt_pyramid_roi_align_forward(int dim, const float *const *images, const int64_t *image_strides, const int *image_dims, int nlevels, const float *boxes,
+                                  const int *box_ind, const int *roi_level, int num_boxes, int batch, int ch, int cw, int cz, int depth, float *crops,
+                                  const int64_t *crop_strides, void *stream) {
+    float *const *maps = const_cast<float *const *>(reinterpret_cast<const float *const *>(images));
+    if (dim == 3) return mdt::pyramid_run<3>(false, maps, image_strides, image_dims, nlevels, nullptr, boxes, box_ind, roi_level, num_boxes, batch, ch, cw, cz,
+                                             depth, crops, crop_strides, 0, nullptr, mdt::as_stream(stream));
+    if (dim == 2) return mdt::pyramid_run<2>(false, maps, image_strides, image_dims, nlevels, nullptr, boxes, box_ind, roi_level, num_boxes, batch, ch, cw, 1,
+                                             depth, crops, crop_strides, 0, nullptr, mdt::as_stream(stream));
+    return MDT_EINVAL;
+}
+int mdt_pyramid_roi_align_backward(int dim, const float *grads, const int64_t *grad_strides, const float *boxes, const int *box_ind, const int *roi_level,
+                                   int num_boxes, int batch, int ch, int cw, int cz, int depth, float *const *grad_images, const int64_t *image_strides,
+                                   const int *image_dims, int nlevels, int zero_init, const int64_t *image_numel, void *stream) {
+    if (dim == 3) return mdt::pyramid_run<3>(true, grad_images, image_strides, image_dims, nlevels, grads, boxes, box_ind, roi_level, num_boxes, batch, ch, cw,
+                                             cz, depth, nullptr, grad_strides, zero_init, image_numel, mdt::as_stream(stream));
+    if (dim == 2) return mdt::pyramid_run<2>(true, grad_images, image_strides, image_dims, nlevels, grads, boxes, box_ind, roi_level, num_boxes, batch, ch, cw,
+                                             1, depth, nullptr, grad_strides, zero_init, image_numel, mdt::as_stream(stream));
+    return MDT_EINVAL;
+}
 
 int mdt_crop_and_resize_3d_forward(const float *image, const int64_t *is, const float *boxes, const int *box_ind, int num_boxes, int batch, int H, int W,
                                    int Z, int ch, int cw, int cz, int depth, float /*extrapolation_value*/, float *crops, const int64_t *os, void *stream) {

@@ -119,11 +119,13 @@ def anchor_delta_targets_device(anchors_dev, gt_boxes_dev, argmax, pos_ids, n_po
     return out
 
 
-def gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids=None, device=None, rng=None):
+def gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids=None, device=None, rng=None, return_pos=False):
     """Device-resident twin of gt_anchor_matching: same semantics, returns CUDA tensors (matches int32 [A], targets float64 [T, 2*dim]).
 
     rng: object with .choice(ids, extra, replace=False) used for the positive sub-sampling of model_utils.py:566-571; defaults to the
     numpy global RNG so that a seeded run reproduces the reference's stream exactly.
+    return_pos: also return the ascending indices of the positive anchors (int64 CUDA) — the loss functions then need no search over the
+    anchor array for them.
     """
     dim = cf.dim
     if device is None:
@@ -133,7 +135,8 @@ def gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids=None, device=N
     T = cf.rpn_train_anchors_per_image
     if gt_boxes is None or len(gt_boxes) == 0:
         # model_utils.py:525-527 (gt_boxes is None): all negative, zero targets
-        return (torch.full((A,), -1, dtype=torch.int32, device=device), torch.zeros((T, 2 * dim), dtype=torch.float64, device=device))
+        out = (torch.full((A,), -1, dtype=torch.int32, device=device), torch.zeros((T, 2 * dim), dtype=torch.float64, device=device))
+        return out + (torch.zeros(0, dtype=torch.long, device=device),) if return_pos else out
     g_dev = torch.as_tensor(np.asarray(gt_boxes, dtype=np.float64)).reshape(-1, 2 * dim).to(device) if not torch.is_tensor(gt_boxes) \
         else gt_boxes.to(device=device, dtype=torch.float64).contiguous()
     c_dev = None
@@ -150,7 +153,7 @@ def gt_anchor_matching_device(cf, anchors, gt_boxes, gt_class_ids=None, device=N
         matches[torch.as_tensor(drop, device=device, dtype=torch.long)] = 0
         pos_ids = torch.nonzero(matches > 0).squeeze(1)
     targets = anchor_delta_targets_device(a_dev, g_dev, argmax, pos_ids.int().contiguous(), pos_ids.numel(), T, cf.rpn_bbox_std_dev, dim)
-    return matches, targets
+    return (matches, targets, pos_ids) if return_pos else (matches, targets)
 
 
 def gt_anchor_matching(cf, anchors, gt_boxes, gt_class_ids=None):

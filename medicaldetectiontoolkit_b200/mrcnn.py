@@ -120,14 +120,14 @@ class Mask(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------------------------------ losses
-def compute_rpn_class_loss(rpn_match, rpn_class_logits, shem_poolsize, max_pos=None):
+def compute_rpn_class_loss(rpn_match, rpn_class_logits, shem_poolsize, max_pos=None, pos_ids=None):
     """CE(positives -> 1) + CE(SHEM negatives -> 0), halved (mrcnn.py:176-213); fixed-shape, sync-free (see retina_unet.compute_class_loss)"""
-    return _shem_class_loss(rpn_match, rpn_class_logits, shem_poolsize=shem_poolsize, max_pos=max_pos)
+    return _shem_class_loss(rpn_match, rpn_class_logits, shem_poolsize=shem_poolsize, max_pos=max_pos, pos_ids=pos_ids)
 
 
-def compute_rpn_bbox_loss(rpn_target_deltas, rpn_pred_deltas, rpn_match, max_pos=None):
+def compute_rpn_bbox_loss(rpn_target_deltas, rpn_pred_deltas, rpn_match, max_pos=None, pos_ids=None):
     """smooth-L1 on positive anchors (mrcnn.py:216-235)"""
-    return _pos_bbox_loss(rpn_target_deltas, rpn_pred_deltas, rpn_match, max_pos=max_pos)
+    return _pos_bbox_loss(rpn_target_deltas, rpn_pred_deltas, rpn_match, max_pos=max_pos, pos_ids=pos_ids)
 
 
 def compute_mrcnn_class_loss(target_class_ids, pred_class_logits):
@@ -196,18 +196,10 @@ def pyramid_roi_align(feature_maps, rois, pool_size, pyramid_levels, dim):
     roi_level = (4 + torch.log2(torch.sqrt(h * w))).round().int().clamp(pyramid_levels[0], pyramid_levels[-1])
     if len(pyramid_levels) == 5:
         roi_level[h * w > 0.65] = 5
-    fn = (ra2D(pool_size[0], pool_size[1], 0) if len(pool_size) == 2 else ra3D(pool_size[0], pool_size[1], pool_size[2], 0))
-    n = rois.shape[0]
-    C = feature_maps[0].shape[1]
-    mf = torch.channels_last_3d if dim == 3 else torch.channels_last
-    pooled = torch.zeros((n, C) + tuple(pool_size), dtype=feature_maps[0].dtype, device=rois.device).contiguous(memory_format=mf)
-    ind_all = batch_ixs.int()
-    for level_ix, level in enumerate(pyramid_levels):
-        # boxes of other levels get box_ind = -1: the kernel writes zeros for them (crop_and_resize_kernel.cu:43-47), so the per-level
-        # results can simply be summed — no nonzero()/index gather, no host sync, one launch per level.
-        ind = torch.where(roi_level == level, ind_all, ind_all.new_full((), -1))
-        pooled = pooled + fn(feature_maps[level_ix], boxes.detach(), ind)
-    return pooled
+    # ONE launch over all levels (csrc/roi_align.cu roi_cl4_pyramid): the RoI's CTA reads the geometry of its own level — no boolean-mask
+    # gather, no per-level launches, no concat + un-permute (mrcnn.py:405-452), each output row written once
+    level_ix = (roi_level - pyramid_levels[0]).clamp(0, len(feature_maps) - 1)
+    return native_ops.pyramid_roi_align(list(feature_maps), boxes.detach(), batch_ixs.int(), level_ix, pool_size)
 
 
 def detection_target_layer(batch_proposals, batch_mrcnn_class_scores, batch_gt_class_ids, batch_gt_boxes, batch_gt_masks, cf):
@@ -448,14 +440,15 @@ class net(nn.Module):
             if len(gt_boxes[b]) > 0:
                 for ix in range(len(gt_boxes[b])):
                     box_results_list[b].append({'box_coords': gt_boxes[b][ix], 'box_label': gt_class_ids[b][ix], 'box_type': 'gt'})
-                rpn_match, rpn_target_deltas = mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b])   # class-agnostic
+                rpn_match, rpn_target_deltas, pos_ids = mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], return_pos=True)   # class-agnostic
             else:
                 rpn_match = torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device)
                 rpn_target_deltas = torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device)
-            cl, neg_ix = compute_rpn_class_loss(rpn_match, rpn_class_logits[b], cf.shem_poolsize, max_pos=max_pos)
+                pos_ids = torch.zeros(0, dtype=torch.long, device=img.device)
+            cl, neg_ix = compute_rpn_class_loss(rpn_match, rpn_class_logits[b], cf.shem_poolsize, max_pos=max_pos, pos_ids=pos_ids)
             monitor.append((rpn_match, neg_ix))
             rpn_class_loss = rpn_class_loss + cl / n_b
-            rpn_bbox_loss = rpn_bbox_loss + compute_rpn_bbox_loss(rpn_target_deltas, rpn_pred_deltas[b], rpn_match, max_pos=max_pos) / n_b
+            rpn_bbox_loss = rpn_bbox_loss + compute_rpn_bbox_loss(rpn_target_deltas, rpn_pred_deltas[b], rpn_match, max_pos=max_pos, pos_ids=pos_ids) / n_b
         if kwargs.get('monitor_anchors', True):
             # positive / sampled-negative anchors of the RPN loss for the monitoring plots (mrcnn.py:896-916)
             sp = img.shape[2:]

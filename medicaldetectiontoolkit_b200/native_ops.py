@@ -134,6 +134,74 @@ class _CropAndResize(torch.autograd.Function):
         return grad_image, None, None, None, None
 
 
+class _PyramidRoIAlign(torch.autograd.Function):
+    """RoIAlign of every RoI on its own pyramid level in ONE kernel launch (mdt_pyramid_roi_align_{forward,backward}); gradient to the maps"""
+
+    @staticmethod
+    def forward(ctx, boxes, box_ind, roi_level, crop_size, *maps):
+        lib = L.load()
+        L.require_cuda(boxes, box_ind, roi_level, *maps)
+        dim = len(crop_size)
+        mf = torch.channels_last_3d if dim == 3 else torch.channels_last
+        maps = [m.contiguous(memory_format=mf) for m in maps]
+        B, C = maps[0].shape[0], maps[0].shape[1]
+        n = boxes.shape[0]
+        boxes = boxes.detach().contiguous().float()
+        box_ind = box_ind.contiguous().int()
+        roi_level = roi_level.contiguous().int()
+        crops = torch.empty((n, C) + tuple(crop_size), dtype=torch.float32, device=boxes.device).contiguous(memory_format=mf)
+        nl = len(maps)
+        ptrs = (ctypes.c_void_p * nl)(*[m.data_ptr() for m in maps])
+        strides = L.i64arr([s for m in maps for s in (tuple(m.stride()) + (0,) * (5 - m.dim()))])
+        dims = (ctypes.c_int * (3 * nl))(*[d for m in maps for d in (tuple(m.shape[2:]) + (1,) * (5 - m.dim()))])
+        cz = crop_size[2] if dim == 3 else 1
+        with torch.cuda.device(boxes.device):
+            rc = lib.mdt_pyramid_roi_align_forward(dim, ptrs, strides, dims, nl, L.ptr(boxes), L.ptr(box_ind), L.ptr(roi_level), n, B, crop_size[0],
+                                                   crop_size[1], cz, C, L.ptr(crops), L.i64arr(tuple(crops.stride()) + (0,) * (5 - crops.dim())),
+                                                   L.stream_ptr())
+        L.check(rc)
+        ctx.save_for_backward(boxes, box_ind, roi_level)
+        ctx.meta = (tuple(crop_size), [tuple(m.shape) for m in maps], [tuple(m.stride()) for m in maps], dim)
+        return crops
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        boxes, box_ind, roi_level = ctx.saved_tensors
+        crop_size, shapes, strides_, dim = ctx.meta
+        lib = L.load()
+        mf = torch.channels_last_3d if dim == 3 else torch.channels_last
+        g = grad_out.detach().float().contiguous(memory_format=mf)
+        grads = [torch.empty_strided(sh, st, dtype=torch.float32, device=g.device) for sh, st in zip(shapes, strides_)]
+        nl = len(grads)
+        ptrs = (ctypes.c_void_p * nl)(*[m.data_ptr() for m in grads])
+        strides = L.i64arr([s for st in strides_ for s in (tuple(st) + (0,) * (5 - len(st)))])
+        dims = (ctypes.c_int * (3 * nl))(*[d for sh in shapes for d in (tuple(sh[2:]) + (1,) * (5 - len(sh)))])
+        numel = L.i64arr([m.numel() for m in grads])
+        cz = crop_size[2] if dim == 3 else 1
+        with torch.cuda.device(g.device):
+            L.check(lib.mdt_pyramid_roi_align_backward(dim, L.ptr(g), L.i64arr(tuple(g.stride()) + (0,) * (5 - g.dim())), L.ptr(boxes), L.ptr(box_ind),
+                                                       L.ptr(roi_level), boxes.shape[0], shapes[0][0], crop_size[0], crop_size[1], cz, shapes[0][1], ptrs,
+                                                       strides, dims, nl, 1, numel, L.stream_ptr()))
+        return (None, None, None, None) + tuple(grads)
+
+
+def pyramid_roi_align(maps, boxes, box_ind, roi_level, crop_size):
+    """crops [n, C, *crop_size] (channels-last) of RoI n taken from maps[roi_level[n]]; one launch; falls back to per-level launches (summed,
+    rows of other levels are zero) when a map layout is outside the vector kernel"""
+    try:
+        return _PyramidRoIAlign.apply(boxes, box_ind, roi_level, tuple(int(c) for c in crop_size), *maps)
+    except L.MdtError as e:
+        if "unsupported" not in str(e).lower():
+            raise
+    fn = (CropAndResizeFunction if len(crop_size) == 3 else CropAndResizeFunction2D)(*crop_size, 0)
+    out = None
+    for lv, m in enumerate(maps):
+        ind = torch.where(roi_level == lv, box_ind, box_ind.new_full((), -1))
+        y = fn(m, boxes, ind)
+        out = y if out is None else out + y
+    return out
+
+
 def _storage_extent(size, stride):
     ext = 1
     for s, st in zip(size, stride):

@@ -86,6 +86,9 @@ def test_class_loss_vs_reference(funcs):
         if lg.shape[1] == 3 and n_pos > 0:
             loss2, _ = retina_unet.compute_class_loss(T(m), T(lg), pool, max_pos=n_pos + 2)
             assert abs(float(loss2) - want) <= 1e-5 * max(1.0, abs(want)), name
+            # ... and so must the path fed with the matching's own list of positives (no search over the anchor array)
+            loss3, neg3 = retina_unet.compute_class_loss(T(m), T(lg), pool, max_pos=n_pos, pos_ids=torch.nonzero(T(m) > 0).squeeze(1))
+            assert abs(float(loss3) - want) <= 1e-5 * max(1.0, abs(want)) and _np(neg3)[_np(neg3) >= 0].tolist() == got_neg.tolist(), name
 
 
 def test_bbox_loss_vs_reference(funcs):
