@@ -303,7 +303,7 @@ constexpr int kMaxChain = 512;
 static int wg_splits(const ConvGeom &g, const WgPlan &w) {
     const long long units = (long long)g.n * g.od * g.oh * w.segs;
     const int mmas_per_unit = w.ksteps * 2;                         // two MMAs per K step go into the same accumulator (x_hi, x_lo)
-    long long max_units = kMaxChain / mmas_per_unit;
+    long long max_units = (getenv("MDT_WG_CHAIN") ? atoi(getenv("MDT_WG_CHAIN")) : kMaxChain) / mmas_per_unit;   // MDT_WG_CHAIN: experiment knob
     if (max_units < 1) max_units = 1;
     const long long min_splits = ceil_div<long long>(units, max_units);
     long long splits = (long long)num_sms() * w.waves / ((long long)w.groups * w.mtiles);   // w.waves CTAs per SM, co-resident

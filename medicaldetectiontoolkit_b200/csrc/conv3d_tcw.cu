@@ -70,6 +70,7 @@ struct TcwParams {
     __nv_bfloat16 *out_split;   // optional: the result also as (hi, lo) bf16 planes in the canonical split layout [line][plane][w][Kg_out]
     int out_split_kg;
     int prof;
+    int skip;                   // diagnostics (MDT_TCW_SKIP): 1 = no MMAs issued (TMA pipeline alone), 2 = no TMA loads (MMA + epilogue alone); results are garbage
     TcwSched sch;
 };
 
@@ -368,11 +369,14 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                             const uint32_t qd = __umulhi(b_seq, p.inv_sb), slot = b_seq - qd * p.SB;
                             { TCW_T0(prof); mbar_wait(&b_empty[slot], (qd & 1) ^ 1); TCW_ACC(prof, pw_b); }
                             uint8_t *bt = smem_b + (size_t)slot * p.b_tile_bytes;
-                            mbar_arrive_expect_tx(&b_full[slot], (uint32_t)p.b_tx);
-                            for (int c = 0; c < p.nchunk; ++c)
-                                for (int pl = 0; pl < p.planes; ++pl)
-                                    tma_load_4d(bt + p.b_off[c] + (size_t)pl * p.NW * 2 * p.cw[c], &maps.b[p.tm[c]], &b_full[slot], p.ck0[c], 0, pl,
-                                                tap_base + kh);
+                            if (p.skip == 2) mbar_arrive(&b_full[slot]);
+                            else {
+                                mbar_arrive_expect_tx(&b_full[slot], (uint32_t)p.b_tx);
+                                for (int c = 0; c < p.nchunk; ++c)
+                                    for (int pl = 0; pl < p.planes; ++pl)
+                                        tma_load_4d(bt + p.b_off[c] + (size_t)pl * p.NW * 2 * p.cw[c], &maps.b[p.tm[c]], &b_full[slot], p.ck0[c], 0, pl,
+                                                    tap_base + kh);
+                            }
                             ++b_seq;
                             ++next_load;
                         }
@@ -381,9 +385,12 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                         uint8_t *as = smem_a + (size_t)slot * p.a_stage_bytes;
                         // one box = both planes of the source line: {chunk, 128 voxels, planes, 1, 1}; rows past the line end and lines outside
                         // the image are TMA zero fill (= the conv's zero padding)
-                        mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx);
-                        for (int c = 0; c < p.nchunk; ++c)
-                            tma_load_5d(as + p.a_off[c], &maps.a[p.tm[c]], &a_full[slot], p.ck0[c], 0, 0, line_base + p.sch.line_rel[i], nb * p.SD + d_src);
+                        if (p.skip == 2) mbar_arrive(&a_full[slot]);
+                        else {
+                            mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx);
+                            for (int c = 0; c < p.nchunk; ++c)
+                                tma_load_5d(as + p.a_off[c], &maps.a[p.tm[c]], &a_full[slot], p.ck0[c], 0, 0, line_base + p.sch.line_rel[i], nb * p.SD + d_src);
+                        }
                         ++a_seq;
                     }
                 }
@@ -437,7 +444,8 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                             if (!acc) { TCW_T0(prof); mbar_wait(&acc_empty[buf][t], bpar ^ 1); TCW_ACC(prof, mw_c); tc_fence_after(); }
                             const uint32_t b16 = sb16 + slot_b * b_tile16;
                             const uint32_t d_tmem = tmem + (buf * (uint32_t)p.TL + t) * (uint32_t)p.ACC;
-                            if (mode == 2) tcw_issue_pair_n<2>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
+                            if (p.skip == 1) { if (!acc) umma2(d_tmem, a16 | (1u << 16), b16 | (1u << 16), desc_hi, idescN, 0); }
+                            else if (mode == 2) tcw_issue_pair_n<2>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
                             else if (mode == 3) tcw_issue_pair_n<3>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
                             else tcw_issue_pair_n<1>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
                             acc_started |= 1u << t;
@@ -788,6 +796,7 @@ int conv_tcw_run(const ConvGeom &g, int pass, const float *src, const float *w, 
     p.out_split = out_split; p.out_split_kg = conv_tc_kpad(pl.Nc);
     p.sch = pl.sch;
     p.prof = tcw_env("MDT_TCW_PROF", 0);
+    p.skip = tcw_env("MDT_TCW_SKIP", 0);
 
     TcwMaps maps;
     memset(&maps, 0, sizeof(maps));

@@ -37,7 +37,8 @@ def main():
         w = torch.randn(cout, cin, *k3, device=dev) * 0.05
         y = C.conv3d_forward(x, w, None, st, p3)          # caches the split form of x on the tensor
         gy = torch.randn_like(y)
-        fn = (lambda: C.conv3d_forward(x, w, None, st, p3, relu=True)) if ps == 0 else (lambda: C.conv3d_dgrad(gy, w, tuple(x.shape), st, p3))
+        fn = {0: (lambda: C.conv3d_forward(x, w, None, st, p3, relu=True)), 1: (lambda: C.conv3d_dgrad(gy, w, tuple(x.shape), st, p3)),
+              2: (lambda: C.conv3d_wgrad(x, gy, tuple(w.shape), st, p3, False))}[ps]
         flops = 2.0 * y.numel() * cin * np.prod(k3)
         if once:
             fn()
