@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
     // when the grid stride is a multiple of `groups`, a thread keeps the same 8 channels for all its rows: column sums then live in
     // registers and touch shared memory once per thread instead of once per element
     const bool reg_sum = colsum && ((long long)gridDim.x * blockDim.x) % groups == 0;
+    const bool vec4 = (C & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(relu_of) | reinterpret_cast<uintptr_t>(masked_out)) & 15) == 0;
     float rs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (colsum) {
         for (int i = threadIdx.x; i < Cp && i < 256; i += blockDim.x) s_sum[i] = 0.f;
@@ -55,16 +56,36 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float *__restrict
         const long long r = i / groups;
         const int c0 = (int)(i % groups) * 8;
         float v[8];
+        if (vec4) {
+            // 128-bit loads / stores: a row is C * 4 bytes with C % 4 == 0 and c0 % 8 == 0, so every 4-channel piece is 16-byte aligned
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            float t = (c0 + k < C) ? __ldg(src + r * C + c0 + k) : 0.f;
-            if (relu_of && c0 + k < C && !(__ldg(relu_of + r * C + c0 + k) > 0.f)) t = 0.f;
-            v[k] = t;
-        }
-        if (masked_out) {
+            for (int h = 0; h < 8; h += 4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c0 + h < C) {
+                    t = __ldg(reinterpret_cast<const float4 *>(src + r * C + c0 + h));
+                    if (relu_of) {
+                        const float4 y = __ldg(reinterpret_cast<const float4 *>(relu_of + r * C + c0 + h));
+                        if (!(y.x > 0.f)) t.x = 0.f;
+                        if (!(y.y > 0.f)) t.y = 0.f;
+                        if (!(y.z > 0.f)) t.z = 0.f;
+                        if (!(y.w > 0.f)) t.w = 0.f;
+                    }
+                    if (masked_out) *reinterpret_cast<float4 *>(masked_out + r * C + c0 + h) = t;
+                }
+                v[h] = t.x; v[h + 1] = t.y; v[h + 2] = t.z; v[h + 3] = t.w;
+            }
+        } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (c0 + k < C) masked_out[r * C + c0 + k] = v[k];
+            for (int k = 0; k < 8; ++k) {
+                float t = (c0 + k < C) ? __ldg(src + r * C + c0 + k) : 0.f;
+                if (relu_of && c0 + k < C && !(__ldg(relu_of + r * C + c0 + k) > 0.f)) t = 0.f;
+                v[k] = t;
+            }
+            if (masked_out) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (c0 + k < C) masked_out[r * C + c0 + k] = v[k];
+            }
         }
         if (reg_sum) {
 #pragma unroll

@@ -43,6 +43,7 @@ struct TcWgradParams {
     long long units;                 // NB * OD * OH * segs
     float *partial;                  // [split][group][mtile][128 lanes][512 cols] fp32 accumulator dumps (reduced by wgrad_reduce_kernel)
     int mtiles;
+    int skip;                        // diagnostics (MDT_WG_SKIP): 1 = no MMAs (TMA pipeline alone), 2 = no TMA loads (MMAs alone); results are garbage
 };
 
 constexpr int kWgThreads = 192;
@@ -109,6 +110,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                     const int d = od * p.sd - p.pd + kd, h = oh * p.sh - p.ph + kh;
                     if (d >= 0 && d < p.D && h >= 0 && h < p.H) bytes += p.planes * p.x_tx_bytes;
                 }
+                if (p.skip == 2) { mbar_arrive(&full[s]); continue; }
                 mbar_arrive_expect_tx(&full[s], bytes);
                 for (int pl = 0; pl < p.planes; ++pl)
                     for (int mc = 0; mc < p.nmc; ++mc)
@@ -156,7 +158,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                     uint64_t dxh = xtmpl | (uint64_t)(((x0 + b * p.x_buf_bytes) >> 4) & 0x3FFF);
                     uint64_t dxl = xtmpl | (uint64_t)(((x0 + b * p.x_buf_bytes + p.x_plane_bytes) >> 4) & 0x3FFF);
                     uint32_t acc = (started >> b) & 1u;
-                    for (int k = 0; k < p.ksteps; ++k) {
+                    for (int k = 0; k < (p.skip == 1 ? 1 : p.ksteps); ++k) {
                         umma_bf16(dcol, dyh, dxh, idesc, acc);
                         if (p.planes > 1) {
                             umma_bf16(dcol, dyh, dxl, idesc, 1);
@@ -370,6 +372,7 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     p.units = (long long)g.n * g.od * g.oh * w.segs;
     p.splits = wg_splits(g, w);
     p.mtiles = w.mtiles;
+    p.skip = getenv("MDT_WG_SKIP") ? atoi(getenv("MDT_WG_SKIP")) : 0;
     p.slot_cols = wg_slot_cols(g, w);
     p.partial = reinterpret_cast<float *>(base + wg_align((size_t)planes * rows_y * co_g * 2) + wg_align((size_t)planes * rows_x * ci_g * 2));
 
@@ -444,6 +447,14 @@ int conv_tc_backward(const ConvGeom &g, const float *x, const float *dy, const f
     }
     long long blocks = ceil_div<long long>(rows_y * (co_p / 8), 256);
     if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    if (db) {
+        // the kernel keeps the column sums (bias gradient) in registers only if a thread stays on the same 8-channel group across its grid-stride
+        // steps, i.e. gridDim * 256 is a multiple of co_p / 8 (6 groups for 36 -> 48 channels): round the grid down to such a size
+        const long long groups = co_p / 8;
+        long long unit = groups;
+        for (long long a = groups, b = 256; b;) { const long long t = a % b; a = b; b = t; unit = groups / a; }   // groups / gcd(groups, 256)
+        if (blocks > unit) blocks = blocks / unit * unit;
+    }
     split_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, ys, rows_y, g.cout, co_p, planes, g.ow, relu_of, dy_masked_out, db);
     int rc = launch_status();
     if (rc) return rc;

@@ -44,6 +44,20 @@ def main():
         y = fn(xg, tb, ti)
         torch.autograd.grad(y, xg, g)
     jobs.append(roi)
+    # pyramid RoIAlign: BASELINE cfg3 (four FPN levels of a 128^3 patch, 2 x 512 proposals, pool 7x7x3), one launch forward + one backward
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import golden_inputs as GI
+    fm, rois = GI.pyramid_inputs("cfg3")
+    fmt = [torch.from_numpy(f).to(DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True) for f in fm]
+    rt = torch.from_numpy(rois).to(DEV)
+    hh, ww = rt[:, 2] - rt[:, 0], rt[:, 3] - rt[:, 1]
+    lvl = (4 + torch.log2(torch.sqrt(hh * ww))).round().int().clamp(0, 3)
+    gp = torch.randn(1024, 36, 7, 7, 3, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+
+    def pyr():
+        y = NO.pyramid_roi_align(fmt, rt[:, :6].contiguous(), rt[:, 6].int(), lvl, (7, 7, 3))
+        torch.autograd.grad(y, fmt, gp)
+    jobs.append(pyr)
     # matching
     anchors = MU.generate_pyramid_anchors(None, cf3d((128, 128, 128)))
     gt = rand_gt(np.random.RandomState(8), 8, (128, 128, 128), 3, 4, 48).astype(np.float64)
@@ -51,9 +65,10 @@ def main():
     a, g_, c_ = torch.from_numpy(anchors).to(DEV), torch.from_numpy(gt).to(DEV), torch.from_numpy(cls).to(DEV)
     jobs.append(lambda: MU.anchor_match_device(a, g_, c_, 3, 0.01, 0.5))
     # conv layers
-    for cin, cout, k, st, pad in [(36, 36, 3, (1, 1, 1), 1), (18, 18, 3, (1, 1, 1), 1), (1, 18, 3, (1, 1, 1), 1), (18, 18, 7, (2, 2, 1), 3)]:
+    for cin, cout, k, st, pad, sp in [(36, 36, 3, (1, 1, 1), 1, (128, 128, 128)), (18, 18, 3, (1, 1, 1), 1, (128, 128, 128)), (1, 18, 3, (1, 1, 1), 1, (128, 128, 128)),
+                                      (18, 18, 7, (2, 2, 1), 3, (128, 128, 128)), (64, 64, 3, (1, 1, 1), 1, (32, 32, 128))]:
         k3, p3 = C._triple(k), C._triple(pad)
-        xc = torch.randn(2, cin, 128, 128, 128, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+        xc = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
         w = torch.randn(cout, cin, *k3, device=DEV) * 0.05
         b = torch.zeros(cout, device=DEV)
         y = C.conv3d_forward(xc, w, b, st, p3, relu=True)
