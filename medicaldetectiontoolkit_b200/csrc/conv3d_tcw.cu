@@ -31,7 +31,7 @@
 namespace mdt {
 using namespace tc;
 
-constexpr int kTcwThreads = 320;   // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kTcwThreads = 352;   // warp 0 producer, warps 1-2 MMA issuers (one per output-line accumulator), warps 3..10 epilogue (two per TMEM lane quarter)
 constexpr int kTcwMaxChunks = 4;
 constexpr int kTcwMaxOps = 12;      // K16 steps per (line, tap) pair: Kg <= 192
 constexpr int kTcwMaxLines = 16;
@@ -330,8 +330,8 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
     const int ct = min(p.CT, p.Cn - n0);   // channels of this N tile
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < p.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < p.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], p.TL); }      // every MMA issuer releases every stage
+        for (int i = 0; i < p.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], p.TL); }
         for (int b = 0; b < 2; ++b)
             for (int i = 0; i < p.TL; ++i) { mbar_init(&acc_full[b][i], 1); mbar_init(&acc_empty[b][i], 8); }
         fence_barrier_init();
@@ -398,23 +398,31 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
             if (prof) { g_tcw_prof[0] += pw_a; g_tcw_prof[1] += pw_b; g_tcw_prof[2] += clock64() - p_start; }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // =============================================================== MMA issuer: ONE elected lane runs the whole role inside a single elect
+    } else if (warp <= 2) {
+        // =============================================================== MMA issuers: warp 1 owns output line t = 0, warp 2 line t = 1 (idle when TL = 1).
+        // Two issuing threads because one thread's fixed costs per pipeline event (a barrier wait ~230 cycles even when complete, a
+        // tcgen05.commit ~80, profiles/r02_tcw_skip.txt + r02_mma_pipe_probe.txt) exceed the MMA time of the event: with one issuer the tensor pipe
+        // sat idle 57 % of the time; two issuers overlap each other's waits.  Each walks the same schedule, issues only the pairs of its own
+        // line and arrives on every release barrier (count = TL).
+        // ONE elected lane runs the whole role inside a single elect
         // region.  Measured (tools/mma_pipe_probe.cu, profiles/r02_mma_pipe_probe.txt): every separate `if (elect) { tcgen05.mma ... }` region
         // costs ~220-300 dead cycles after its last MMA (+80 per tcgen05.commit) during which the queued MMAs drain — 48 such regions per tile
         // were 45 % of this kernel's time; inside one region MMAs issue back to back at the operand-bandwidth rate.
-        if (elect_one()) {
+        const uint32_t my_t = (uint32_t)(warp - 1);
+        if (my_t < (uint32_t)p.TL && elect_one()) {
             const uint32_t idescN = make_idesc_bf16(128, p.NW, 0, 0);
             const uint32_t idesc2N = make_idesc_bf16(128, 2 * p.NW, 0, 0);
             const uint32_t sa16 = smem_u32(smem_a) >> 4, sb16 = smem_u32(smem_b) >> 4;
             const uint32_t a_stage16 = (uint32_t)p.a_stage_bytes >> 4, b_tile16 = (uint32_t)p.b_tile_bytes >> 4;
             const int mode = p.stacked ? 2 : (p.planes > 1 ? 3 : 1);
             // all chunks are 64 channels x 128B swizzle: chunk strides / plane offsets in 16-byte units, one descriptor high word
-            const uint32_t chunk_a16 = (uint32_t)(p.planes * 128 * 128) >> 4, chunk_b16 = (uint32_t)(p.planes * p.NW * 128) >> 4;
-            const uint32_t alo16 = (128u * 128u) >> 4, blo16 = ((uint32_t)p.NW * 128u) >> 4;
-            const uint32_t desc_hi = ((8u * 128u) >> 4) | (1u << 14) | (layout_type_for_swizzle_bytes(128) << 29);
+            // (a single narrower chunk — 32 or 16 channels, 64B / 32B swizzle — under MDT_TCW_NARROW: same formulas with its row width)
+            const uint32_t swz = 2u * (uint32_t)p.cw[0];
+            const uint32_t chunk_a16 = ((uint32_t)p.planes * 128u * swz) >> 4, chunk_b16 = ((uint32_t)(p.planes * p.NW) * swz) >> 4;
+            const uint32_t alo16 = (128u * swz) >> 4, blo16 = ((uint32_t)p.NW * swz) >> 4;
+            const uint32_t desc_hi = ((8u * swz) >> 4) | (1u << 14) | (layout_type_for_swizzle_bytes((int)swz) << 29);
             uint32_t a_seq = 0, b_seq = 0, it = 0;
-            const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0;
+            const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && my_t == 0;
             long long mw_a = 0, mw_b = 0, mw_c = 0;
             const long long m_start = prof ? clock64() : 0;
             for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -439,18 +447,20 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                             const uint32_t t = pwd & 0xffu, fl = (pwd >> 16) & 0xffu;
                             const uint32_t bs = b_seq + (pwd >> 24);
                             const uint32_t qb = __umulhi(bs, p.inv_sb), slot_b = bs - qb * p.SB;
-                            if (fl & kFlagFirst) { TCW_T0(prof); mbar_wait(&b_full[slot_b], qb & 1); TCW_ACC(prof, mw_b); tc_fence_after(); }
-                            uint32_t acc = (acc_started >> t) & 1u;
-                            if (!acc) { TCW_T0(prof); mbar_wait(&acc_empty[buf][t], bpar ^ 1); TCW_ACC(prof, mw_c); tc_fence_after(); }
-                            const uint32_t b16 = sb16 + slot_b * b_tile16;
-                            const uint32_t d_tmem = tmem + (buf * (uint32_t)p.TL + t) * (uint32_t)p.ACC;
-                            if (p.skip == 1) { if (!acc) umma2(d_tmem, a16 | (1u << 16), b16 | (1u << 16), desc_hi, idescN, 0); }
-                            else if (mode == 2) tcw_issue_pair_n<2>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
-                            else if (mode == 3) tcw_issue_pair_n<3>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
-                            else tcw_issue_pair_n<1>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
-                            acc_started |= 1u << t;
-                            if (fl & kFlagLast) umma_commit(&b_empty[slot_b]);
-                            if (last_kd && (fl & kFlagAccLast)) umma_commit(&acc_full[buf][t]);
+                            if (t == my_t) {
+                                { TCW_T0(prof); mbar_wait(&b_full[slot_b], qb & 1); TCW_ACC(prof, mw_b); tc_fence_after(); }
+                                uint32_t acc = acc_started;
+                                if (!acc) { TCW_T0(prof); mbar_wait(&acc_empty[buf][t], bpar ^ 1); TCW_ACC(prof, mw_c); tc_fence_after(); }
+                                const uint32_t b16 = sb16 + slot_b * b_tile16;
+                                const uint32_t d_tmem = tmem + (buf * (uint32_t)p.TL + t) * (uint32_t)p.ACC;
+                                if (p.skip == 1) { if (!acc) umma2(d_tmem, a16 | (1u << 16), b16 | (1u << 16), desc_hi, idescN, 0); }
+                                else if (mode == 2) tcw_issue_pair_n<2>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
+                                else if (mode == 3) tcw_issue_pair_n<3>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
+                                else tcw_issue_pair_n<1>(p.nops, d_tmem, a16, b16, chunk_a16, chunk_b16, alo16, blo16, desc_hi, idescN, idesc2N, acc);
+                                acc_started = 1;
+                                if (last_kd && (fl & kFlagAccLast)) umma_commit(&acc_full[buf][t]);
+                            }
+                            if (fl & kFlagLast) umma_commit(&b_empty[slot_b]);     // both issuers, at the tile's last use in the schedule
                         }
                         umma_commit(&a_empty[slot_a]);
                         ++a_seq;
@@ -462,14 +472,14 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
         }
         __syncwarp();
     } else {
-        // =============================================================== epilogue (warps 2..9: TMEM lane quarter = warp % 4, two warps per quarter)
+        // =============================================================== epilogue (warps 3..10: TMEM lane quarter = warp % 4, two warps per quarter)
         const int q = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 3) >> 2;
         const int r = q * 32 + lane;
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
         const int vecw = (p.Cn % 4 == 0 && n0 % 4 == 0) ? 4 : ((p.Cn % 2 == 0 && n0 % 2 == 0) ? 2 : 1);
         uint32_t it = 0, grp = 0;
-        const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64;
+        const bool prof = p.prof && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 96;
         long long ew = 0;
         const long long e_start = prof ? clock64() : 0;
         for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -655,7 +665,16 @@ static TcwPlan make_tcw_plan(const ConvGeom &g, int pass, int planes) {
     // swizzle, so every chunk is staged as 64 channels x 128B swizzle; a chunk that runs past Kg (36 -> Kg = 48) is zero-filled by the TMA
     // (no L2 traffic for it) and only its first Kg/16 K-steps are issued.
     int k = 0, nc = 0;
-    while (k < pl.Kg) { if (nc == kTcwMaxChunks) return pl; pl.ck0[nc] = k; pl.cw[nc] = 64; pl.cks[nc] = std::min(4, (pl.Kg - k) / 16); pl.tm[nc] = 0; ++nc; k += 64; }
+    const bool narrow = tcw_env("MDT_TCW_NARROW", 1) != 0;   // measured: 18 -> 18 k7 fprop 1.69 -> 1.41 ms (the zero-padded rows made it TMA-bound)
+    while (k < pl.Kg) {
+        if (nc == kTcwMaxChunks) return pl;
+        const int rem = pl.Kg - k;
+        pl.ck0[nc] = k; pl.cw[nc] = 64; pl.cks[nc] = std::min(4, rem / 16); pl.tm[nc] = 0;
+        // a LAST chunk of exactly 32 or 16 channels may be staged at its own width (64B / 32B swizzle): half / quarter the shared-memory fill
+        // of the zero-padded 128-byte rows (MDT_TCW_NARROW=0 switches back; A/B knob)
+        if (narrow && nc == 0 && (rem == 32 || rem == 16)) { pl.cw[nc] = rem; pl.tm[nc] = rem == 32 ? 1 : 2; }
+        ++nc; k += 64;
+    }
     k = pl.Kg;
     if (k != pl.Kg || pl.Kg / 16 > kTcwMaxOps) return pl;
     pl.nchunk = nc;
@@ -669,9 +688,10 @@ static TcwPlan make_tcw_plan(const ConvGeom &g, int pass, int planes) {
     if (pl.NT == 1 && (g.kw * cs4 > 256 || (ceil_div(g.kw * cs2, 16) < ceil_div(g.kw * cs4, 16) && tcw_env("MDT_TCW_LD2", 1)))) { pl.ldw = 2; pl.Cs = cs2; }
     pl.NW = ceil_div(g.kw * pl.Cs, 16) * 16;
     if (pl.NW > 256) return pl;
-    // Where it wins (profiles/r02_tcw_layers.txt): few K steps and wide stacked N (36 -> 36/64 k3, 18 -> 18 k7).  With <= 64 stacked columns or
-    // 4+ K steps the halo-window kernel with 4-5 co-resident CTAs is as fast or faster.  MDT_TCW=2 forces this kernel wherever it is supported.
-    if (tcw_env("MDT_TCW", 1) != 2 && !(pl.Kg <= 48 && pl.NW >= 112)) return pl;
+    // Where it wins (profiles/r02_tcw_vs_halo.txt): >= 112 stacked columns (36 -> 36/64, 64 -> 64/54 k3, 18 -> 18 k7: 1.07x .. 1.84x).  With the 64
+    // stacked columns of the 18-channel 3x3x3 layers the halo-window kernel with 4-5 co-resident CTAs is faster (1.02 vs 1.16 ms).
+    // MDT_TCW=2 forces this kernel wherever it is supported.
+    if (tcw_env("MDT_TCW", 1) != 2 && !(pl.Kg <= 64 && pl.NW >= 112)) return pl;
     // accumulator layout.  "stacked": one MMA of N = 2*NW yields hi*hi and hi*lo side by side (fewer, wider MMAs: wins while 2*NW stays small);
     // prefer whatever leaves room for TWO accumulator sets (epilogue of tile i under the MMAs of tile i + 1)
     pl.TL = pl.RH > 1 ? 2 : 1;

@@ -98,11 +98,11 @@ def test_conv3d_fprop_dgrad_wgrad(cin, cout, k, stride, pad, sp):
 
 
 def test_tap_stacked_kernel_is_selected_for_long_lines():
-    """fprop / dgrad of the long-line layers with few K steps and >= 112 stacked columns (36 -> 36/64 k3, 18 -> 18 k7: where it measured
-    faster, profiles/r02_tcw_layers.txt) run on conv3d_tcw.cu, the others on conv3d_tc.cu"""
+    """fprop / dgrad of the long-line layers with >= 112 stacked columns (36 -> 36/64, 64 -> 64 k3, 18 -> 18 k7: where it measured faster,
+    profiles/r02_tcw_vs_halo.txt) run on conv3d_tcw.cu, the others on conv3d_tc.cu"""
     lib = L.load()
     for cin, cout, k, stride, pad, sp, want in [(36, 36, 3, 1, 1, (128, 128, 128), [3, 3]), (18, 18, 7, (2, 2, 1), 3, (128, 128, 128), [3, 3]),
-                                                (36, 64, 3, 1, 1, (32, 32, 128), [3, 2]), (64, 64, 3, 1, 1, (32, 32, 128), [2, 2]),
+                                                (36, 64, 3, 1, 1, (32, 32, 128), [3, 3]), (64, 64, 3, 1, 1, (32, 32, 128), [3, 3]),
                                                 (18, 18, 3, 1, 1, (128, 128, 128), [2, 2]), (64, 64, 3, 1, 1, (16, 16, 64), [2, 2]),
                                                 (144, 144, 3, 1, 1, (8, 8, 32), [2, 2])]:
         d = C._desc((2, cin) + sp, (cout, cin) + C._triple(k), C._triple(stride), C._triple(pad), False, 0, 0)
