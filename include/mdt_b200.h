@@ -125,7 +125,7 @@ typedef struct mdt_conv3d_desc {
     int pd, ph, pw;          /* zero padding */
     int relu;                /* fuse ReLU into the fprop epilogue */
     int precision;           /* 0 = fp32-faithful (3-pass split-bf16 on tcgen05, or fp32 SIMT); 1 = single-pass bf16 (throughput mode) */
-    int algo;                /* 0 = auto, 1 = force SIMT direct kernels, 2 = force tcgen05 implicit GEMM (error if shape unsupported) */
+    int algo;                /* 0 = auto, 1 = force SIMT direct kernels, 2 = force tcgen05 implicit GEMM, 4 = force pointwise streaming (error if unsupported) */
 } mdt_conv3d_desc;
 
 size_t mdt_conv3d_workspace_bytes(const mdt_conv3d_desc *desc_host, int pass /*0 fprop,1 dgrad,2 wgrad*/);
@@ -160,10 +160,15 @@ int mdt_conv3d_fprop_presplit(const mdt_conv3d_desc *desc_host, const void *x_sp
 size_t mdt_conv3d_out_split_bytes(const mdt_conv3d_desc *desc_host);
 int mdt_conv3d_fprop_presplit_out(const mdt_conv3d_desc *desc_host, const void *x_split, const float *w, const float *bias, const float *residual,
                                   float *y, void *y_split, void *workspace, size_t workspace_bytes, void *stream);
-/* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05 */
+/* fp32-input fprop that also emits the split planes of y (as mdt_conv3d_fprop_presplit_out does for a pre-split input): pointwise path only
+ * (mdt_conv3d_algo == 4), else MDT_EUNSUPPORTED.  Used where a 1x1x1 conv feeds a tcgen05 conv (ResBlock conv1 -> conv2, P0_conv1 -> P0_conv2). */
+int mdt_conv3d_fprop_out(const mdt_conv3d_desc *desc_host, const float *x, const float *w, const float *bias, const float *residual, float *y,
+                         void *y_split, void *workspace, size_t workspace_bytes, void *stream);
+/* which algorithm `auto` resolves to for this descriptor/pass: 1 SIMT, 2 tcgen05, 4 pointwise fp32 streaming (1x1x1, stride 1, no padding,
+ * cin * cout <= 2592 under `auto` (where it measured faster than tcgen05), <= 6144 when forced with algo = 4: HBM-bound layers, csrc/conv3d_pw.cu) */
 int mdt_conv3d_algo(const mdt_conv3d_desc *desc_host, int pass);
 /* which kernel family runs this descriptor/pass: 1 fp32 SIMT / direct stem, 2 tcgen05 halo-window implicit GEMM (conv3d_tc.cu, wgrad:
- * conv3d_tc_wgrad.cu), 3 tcgen05 tap-stacked implicit GEMM (conv3d_tcw.cu: fprop/dgrad of lines of 65..128 voxels); 0 = unsupported */
+ * conv3d_tc_wgrad.cu), 3 tcgen05 tap-stacked implicit GEMM (conv3d_tcw.cu: fprop/dgrad of lines of 65..128 voxels), 4 pointwise fp32 streaming (conv3d_pw.cu); 0 = unsupported */
 int mdt_conv3d_variant(const mdt_conv3d_desc *desc_host, int pass);
 /* diagnostics: cycle counters of CTA 0 of the tap-stacked kernel, accumulated while the environment has MDT_TCW_PROF=1 (16 values: producer
  * wait-A / wait-B / total, MMA wait-A / wait-B / wait-accumulator / total, epilogue wait / total, tiles); synchronises the device and clears them */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "mdt_conv3d_fprop_presplit": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_conv3d_out_split_bytes": (_SZ, [ctypes.POINTER(Conv3dDesc)]),
     "mdt_conv3d_fprop_presplit_out": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mdt_conv3d_fprop_out": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_upsample221_forward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mdt_upsample221_backward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
 }

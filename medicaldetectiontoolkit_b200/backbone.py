@@ -10,9 +10,9 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 try:
-    from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
+    from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer, pointwise_eligible
 except ImportError:   # loaded by FILE PATH as the reference does (utils.import_module('bbone', cf.backbone_path), mrcnn.py:842): no parent package
-    from medicaldetectiontoolkit_b200.conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer
+    from medicaldetectiontoolkit_b200.conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer, pointwise_eligible
 
 _CL3 = torch.channels_last_3d
 
@@ -47,6 +47,11 @@ class ResBlock(nn.Module):
             self.downsample = conv(downsample[0], downsample[0] * downsample[1], ks=1, stride=downsample[2], norm=norm, relu=None)
         self.stride = stride
         self._fusable = (relu == 'relu') and norm is None
+        # split planes are emitted for tensor-core consumers only: conv3 (1x1x1) reads fp32 rows when it is pointwise-eligible, and the block
+        # output mostly feeds the next block's 1x1x1 conv1 / a lateral (the few strided or wide consumers split on demand)
+        if pointwise_eligible(planes, planes * 4):
+            no_split_consumer(self.conv2)
+        no_split_consumer(self.conv3)
 
     def forward(self, x):
         shortcut = self.downsample(x) if self.downsample is not None else x

@@ -19,7 +19,7 @@ _CL3 = torch.channels_last_3d
 
 # precision: 0 = fp32-faithful (3-pass split-bf16 on tcgen05 / fp32 SIMT), 1 = single-pass bf16 on tcgen05
 DEFAULT_PRECISION = 0
-# algo: 0 auto, 1 force SIMT, 2 force tcgen05
+# algo: 0 auto, 1 force SIMT, 2 force tcgen05, 4 force the pointwise fp32 streaming kernels (1x1x1 stride 1)
 DEFAULT_ALGO = 0
 
 _ws_cache = {}
@@ -134,6 +134,11 @@ def conv3d_forward(x, weight, bias, stride, padding, relu=False, residual=None, 
             y._mdt_split = (ys, y._version, precision)
         else:
             L.check(lib.mdt_conv3d_fprop_presplit(d, L.ptr(xs), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    elif which == 4 and emit_split and EMIT_SPLIT:
+        # pointwise conv feeding a tcgen05 conv: fp32 rows in, fp32 result + its split planes out
+        ys = torch.empty(lib.mdt_conv3d_out_split_bytes(d), dtype=torch.uint8, device=x.device)
+        L.check(lib.mdt_conv3d_fprop_out(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ys), L.ptr(ws), ws.numel(), L.stream_ptr()))
+        y._mdt_split = (ys, y._version, precision)
     else:
         L.check(lib.mdt_conv3d_fprop(d, L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(residual), L.ptr(y), L.ptr(ws), ws.numel(), L.stream_ptr()))
     _ev_end(ev, (0, tuple(x.shape), tuple(w.shape), tuple(stride), which))
@@ -202,7 +207,7 @@ def conv3d_backward(x, gy, y_relu, weight, stride, padding, need_dx, want_bias, 
     ev = _ev_start()
     L.check(lib.mdt_conv3d_backward(d, L.ptr(x), L.ptr(x_split), L.ptr(gy), L.ptr(y_relu), L.ptr(w), L.ptr(dx), L.ptr(dw), L.ptr(db), L.ptr(gm),
                                     L.ptr(ws), ws.numel(), L.stream_ptr()))
-    _ev_end(ev, (3, tuple(x.shape), tuple(w.shape), tuple(stride), 2))
+    _ev_end(ev, (3, tuple(x.shape), tuple(w.shape), tuple(stride), _plan(lib, d, 2)[1]))
     return dx, dw, db, gm
 
 
@@ -303,6 +308,13 @@ class Conv2d(nn.Module):
         y = _Conv3dFn.apply(x.unsqueeze(2), self.weight.unsqueeze(2), self.bias, res, (1,) + self.stride, (0,) + self.padding,
                             self.fused_relu, self.precision, self.algo)
         return y.squeeze(2)
+
+
+def pointwise_eligible(c_in, c_out, ks=1, stride=1, pad=0):
+    """mirror of conv_pw_supported (csrc/conv3d_pw.cu): 1x1x1 stride-1 convs with cin * cout <= 2592 run on the fp32 streaming kernels, which read
+    fp32 rows: a conv feeding ONLY such convs need not emit split planes"""
+    one = lambda v, t: all(int(i) == t for i in (v if isinstance(v, (tuple, list)) else (v,)))
+    return one(ks, 1) and one(stride, 1) and one(pad, 0) and c_in * c_out <= 2592
 
 
 def no_split_consumer(module):

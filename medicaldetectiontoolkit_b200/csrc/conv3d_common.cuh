@@ -34,6 +34,16 @@ bool conv_stem_supported(const ConvGeom &g, int pass);
 int conv_stem_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, float *y, int relu, cudaStream_t st);
 int conv_stem_wgrad(const ConvGeom &g, const float *x, const float *dy, float *dw, float *db, cudaStream_t st);
 
+// pointwise 1x1x1 stride-1 fp32 streaming kernels (conv3d_pw.cu)
+bool conv_pw_supported(const ConvGeom &g, int pass);
+bool conv_pw_preferred(const ConvGeom &g);   // `auto` picks the pointwise kernels only where they measured faster than tcgen05
+size_t conv_pw_workspace_bytes(const ConvGeom &g, int pass);
+int conv_pw_fprop(const ConvGeom &g, const float *x, const float *w, const float *bias, const float *residual, float *y, int relu, int precision,
+                  void *y_split, cudaStream_t st);
+int conv_pw_dgrad(const ConvGeom &g, const float *dy, const float *relu_of, const float *w, float *dx, float *dy_masked_out, cudaStream_t st);
+int conv_pw_wgrad(const ConvGeom &g, const float *x, const float *dy, const float *relu_of, float *dw, float *db, void *ws, size_t ws_bytes,
+                  cudaStream_t st, float *dy_masked_out = nullptr);
+
 // tcgen05 (conv3d_tc.cu; conv3d_tcw.cu for the tap-stacked variant)
 bool conv_tc_supported(const ConvGeom &g, int pass);
 bool conv_tcw_supported(const ConvGeom &g, int pass);

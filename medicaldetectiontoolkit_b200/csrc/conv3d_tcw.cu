@@ -70,7 +70,7 @@ struct TcwParams {
     __nv_bfloat16 *out_split;   // optional: the result also as (hi, lo) bf16 planes in the canonical split layout [line][plane][w][Kg_out]
     int out_split_kg;
     int prof;
-    int skip;                   // diagnostics (MDT_TCW_SKIP): 1 = no MMAs issued (TMA pipeline alone), 2 = no TMA loads (MMA + epilogue alone); results are garbage
+    int skip;                   // diagnostics (MDT_TCW_SKIP): 1 = no MMAs issued (TMA pipeline alone), 2 = no TMA loads (MMA + epilogue alone), 3 = no epilogue work, 4 = neither TMA nor epilogue (MMA issue + tensor pipe alone); results are garbage
     TcwSched sch;
 };
 
@@ -369,7 +369,7 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                             const uint32_t qd = __umulhi(b_seq, p.inv_sb), slot = b_seq - qd * p.SB;
                             { TCW_T0(prof); mbar_wait(&b_empty[slot], (qd & 1) ^ 1); TCW_ACC(prof, pw_b); }
                             uint8_t *bt = smem_b + (size_t)slot * p.b_tile_bytes;
-                            if (p.skip == 2) mbar_arrive(&b_full[slot]);
+                            if (p.skip == 2 || p.skip == 4) mbar_arrive(&b_full[slot]);
                             else {
                                 mbar_arrive_expect_tx(&b_full[slot], (uint32_t)p.b_tx);
                                 for (int c = 0; c < p.nchunk; ++c)
@@ -385,7 +385,7 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                         uint8_t *as = smem_a + (size_t)slot * p.a_stage_bytes;
                         // one box = both planes of the source line: {chunk, 128 voxels, planes, 1, 1}; rows past the line end and lines outside
                         // the image are TMA zero fill (= the conv's zero padding)
-                        if (p.skip == 2) mbar_arrive(&a_full[slot]);
+                        if (p.skip == 2 || p.skip == 4) mbar_arrive(&a_full[slot]);
                         else {
                             mbar_arrive_expect_tx(&a_full[slot], (uint32_t)p.a_tx);
                             for (int c = 0; c < p.nchunk; ++c)
@@ -493,7 +493,7 @@ conv_tcw_kernel(const __grid_constant__ TcwMaps maps, const __grid_constant__ Tc
                 { TCW_T0(prof); mbar_wait(&acc_full[buf][t], bpar); TCW_ACC(prof, ew); }
                 tc_fence_after();
                 const int rh = th * p.TL + t;
-                if (rh < p.RH) {
+                if (rh < p.RH && p.skip < 3) {
                     const uint32_t acc0 = lane_base + (buf * (uint32_t)p.TL + (uint32_t)t) * (uint32_t)p.ACC;
                     const size_t line_idx = ((size_t)nb * p.RD + rd) * p.RH + rh;
                     const bool row_ok = r < p.RW;

@@ -42,6 +42,13 @@ SHAPES = [
     (18, 36, 3, (2, 2, 1), 1, (6, 8, 128)),    # strided k3
     (36, 36, 3, 1, 0, (5, 6, 128)),            # valid conv: output lines of 126 voxels
     (36, 18, 3, 1, 1, (3, 5, 72)),             # 18 output channels (float2 stores), 72-voxel lines
+    # pointwise fp32 streaming kernels (conv3d_pw.cu, algo 4)
+    (18, 36, 1, 1, 0, (5, 7, 128)),            # P0_conv1 lateral; voxel count not a multiple of the 256-voxel tile
+    (36, 144, 1, 1, 0, (4, 4, 16)),            # ResBlock conv3: 36 output quads = 3 chunks of 12
+    (144, 36, 1, 1, 0, (4, 4, 16)),            # ResBlock conv1 of the next block: one voxel per thread
+    (72, 18, 1, 1, 0, (4, 4, 32)),
+    (64, 96, 1, 1, 0, (3, 3, 16)),             # the largest cin * cout that stays off the tensor cores; two chunks of 12 quads
+    (5, 7, 1, 1, 0, (3, 5, 9)),                # odd channel counts: scalar global accesses, padded quads
 ]
 
 
@@ -79,8 +86,13 @@ def test_conv3d_fprop_dgrad_wgrad(cin, cout, k, stride, pad, sp):
     tc = _tc_passes((tuple(x.shape), tuple(w.shape), s3, p3))
     if cin <= 4:   # stem: `auto` resolves to the direct SIMT kernels; still exercise the tensor-core kernels explicitly
         tc = [0, 1, 2]
-    for algo in (1, 2):
-        for prec in ([0] if algo == 1 else [0, 1]):
+    lib = L.load()
+    pw = [ps for ps in (0, 1, 2) if lib.mdt_conv3d_algo(C._desc(tuple(x.shape), tuple(w.shape), s3, p3, False, 0, 4), ps) == 4]
+    assert bool(pw) == (k3 == (1, 1, 1) and s3 == (1, 1, 1) and cin * cout <= 6144)
+    for algo in (1, 2, 4):
+        if algo == 4:
+            tc = pw
+        for prec in ([0] if algo != 2 else [0, 1]):
             tol = TOL if prec == 0 else 2e-2   # precision 1 = single-pass bf16 throughput mode
             if algo == 1 or 0 in tc:
                 y = C.conv3d_forward(x, w, b, s3, p3, relu=True, precision=prec, algo=algo)
@@ -108,6 +120,21 @@ def test_tap_stacked_kernel_is_selected_for_long_lines():
         d = C._desc((2, cin) + sp, (cout, cin) + C._triple(k), C._triple(stride), C._triple(pad), False, 0, 0)
         assert [lib.mdt_conv3d_variant(d, ps) for ps in (0, 1)] == want, (cin, cout, k, sp)
         assert lib.mdt_conv3d_variant(d, 2) == 2
+
+
+def test_pointwise_layers_run_on_the_streaming_kernels():
+    """1x1x1 stride-1 convs with cin * cout <= 2592 (laterals, the narrow bottleneck 1x1x1s, final_conv: where tools/pw_bench.py measured them
+    faster) resolve to conv3d_pw.cu for all passes and for the fused backward; wider ones and strided ones stay where they were"""
+    lib = L.load()
+    for cin, cout, stride, sp, want in [(18, 36, 1, (128, 128, 128), 4), (36, 2, 1, (128, 128, 128), 4), (18, 72, 1, (32, 32, 128), 4),
+                                        (72, 18, 1, (32, 32, 128), 4), (144, 36, 1, (16, 16, 64), 2), (36, 144, 1, (16, 16, 64), 2), (288, 72, 1, (8, 8, 32), 2), (72, 144, 2, (32, 32, 128), None)]:
+        d = C._desc((2, cin) + sp, (cout, cin, 1, 1, 1), C._triple(stride), (0, 0, 0), False, 0, 0)
+        got = [lib.mdt_conv3d_variant(d, ps) for ps in (0, 1, 2)]
+        if want is None:
+            assert 4 not in got
+        else:
+            assert got == [want] * 3, (cin, cout, got)
+            assert lib.mdt_conv3d_backward_fused(d, 1) == 1
 
 
 def test_tc_path_covers_the_hot_layers():
@@ -153,11 +180,12 @@ def test_conv2d_module_matches_torch():
     assert x.grad is not None and m[0].weight.grad.shape == m[0].weight.shape
 
 
-@pytest.mark.parametrize("cin,cout,sp", [(18, 72, (8, 8, 32)), (64, 64, (4, 8, 128)), (36, 36, (8, 8, 128)), (1, 18, (8, 8, 128))])
+@pytest.mark.parametrize("cin,cout,sp", [(18, 72, (8, 8, 32)), (64, 64, (4, 8, 128)), (36, 36, (8, 8, 128)), (1, 18, (8, 8, 128)), (36, 144, (5, 5, 9)),
+                                         (144, 36, (4, 4, 16))])
 def test_fused_backward_relu_residual_bias(cin, cout, sp):
     """mdt_conv3d_backward: one pass over dy feeds dgrad + wgrad, with the ReLU mask, the bias gradient and the residual gradient folded in"""
     torch.manual_seed(cin + cout)
-    k = 1 if cout == 72 else 3
+    k = 1 if (cin, cout) in ((18, 72), (36, 144), (144, 36)) else 3
     pad = k // 2
     x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d).requires_grad_(cin > 1)
     w = (torch.randn(cout, cin, k, k, k, device=DEV) / np.sqrt(cin * k ** 3)).requires_grad_(True)
@@ -180,7 +208,8 @@ def test_fused_backward_relu_residual_bias(cin, cout, sp):
 
 
 @pytest.mark.parametrize("cin,cout,k,stride,sp", [(36, 36, 3, 1, (3, 5, 128)), (36, 64, 3, 1, (2, 4, 128)), (64, 64, 3, 1, (2, 4, 128)), (64, 54, 3, 1, (4, 8, 32)),
-                                                    (18, 18, 7, (2, 2, 1), (8, 8, 128)), (72, 18, 1, 1, (4, 4, 32)), (18, 72, 1, 1, (3, 4, 128))])
+                                                    (18, 18, 7, (2, 2, 1), (8, 8, 128)), (72, 18, 1, 1, (4, 4, 32)), (18, 72, 1, 1, (3, 4, 128)),
+                                                    (18, 36, 1, 1, (3, 5, 128)), (36, 144, 1, 1, (2, 3, 40)), (144, 288, 1, 1, (2, 2, 16))])
 def test_epilogue_emits_the_split_planes_of_the_result(cin, cout, k, stride, sp):
     """mdt_conv3d_fprop_presplit_out: the (hi, lo) bf16 planes written by the conv epilogue are byte-identical to mdt_conv3d_split applied to
     the fp32 result (incl. zero padding channels), for both tcgen05 fprop kernels; a consumer conv fed from them gives identical output"""
@@ -192,8 +221,8 @@ def test_epilogue_emits_the_split_planes_of_the_result(cin, cout, k, stride, sp)
     w = torch.randn(cout, cin, *k3, device=DEV) / np.sqrt(cin * np.prod(k3))
     b = torch.randn(cout, device=DEV)
     d = C._desc(tuple(x.shape), tuple(w.shape), s3, p3, True, 0, 0)
-    if lib.mdt_conv3d_algo(d, 0) != 2:
-        pytest.skip("shape not on the tcgen05 path")
+    if lib.mdt_conv3d_algo(d, 0) not in (2, 4):
+        pytest.skip("shape on neither the tcgen05 nor the pointwise path")
     y0 = C.conv3d_forward(x, w, b, s3, p3, relu=True)
     y1 = C.conv3d_forward(x, w, b, s3, p3, relu=True, emit_split=True)
     assert torch.equal(y0, y1)

@@ -53,7 +53,7 @@ def main():
         od = [(xs[2 + i] + 0) for i in range(3)]
         mult = 2.0 if ps == 3 else 1.0
         flops = mult * 2.0 * xs[0] * np.prod([xs[2 + i] // st[i] for i in range(3)]) * ws[0] * ws[1] * ws[2] * ws[3] * ws[4]
-        key = (("fprop", "dgrad", "wgrad", "bwd")[ps], xs[1], ws[0], ws[2:], st, xs[2:], "TC" if algo == 2 else "SIMT")
+        key = (("fprop", "dgrad", "wgrad", "bwd")[ps], xs[1], ws[0], ws[2:], st, xs[2:], {2: "TC", 4: "PW"}.get(algo, "SIMT"))
         agg[key][0] += a.elapsed_time(b)
         agg[key][1] += 1
         agg[key][2] += flops
