@@ -179,6 +179,48 @@ int mdt_debug_conv_tcw_prof(unsigned long long *out16_host);
 int mdt_upsample221_forward(const float *x, float *y, int n, int d, int h, int w, int c, void *stream);
 int mdt_upsample221_backward(const float *gy, float *gx, int n, int d, int h, int w, int c, void *stream);
 
+/* ------------------------------------------------------------- pooling / nearest up-sampling -------------------------------------------------
+ * replaces: nn.MaxPool3d(kernel_size=3, stride=(2,2,1), padding=1) / nn.MaxPool2d(3, 2, 1) of models/backbone.py:63-64 (applied at :129) and its
+ * autograd backward.  NDHWC maps (2D: d = 1, kernel {1,3,3}).  x [n,d,h,w,c] -> y [n,od,oh,ow,c] with o = (i + 2p - k) / s + 1 (floor mode);
+ * argmax [n,od,oh,ow,c] holds the winning window offset ((a*kh + b)*kw + e) per element, ATen's update rule (first maximum, NaN propagates).
+ * Backward is a gather over the windows containing an input voxel: no atomics, gx fully written. */
+int mdt_maxpool3d_forward(const float *x, float *y, unsigned char *argmax, int n, int d, int h, int w, int c, const int *kernel3, const int *stride3,
+                          const int *pad3, void *stream);
+int mdt_maxpool3d_backward(const float *gy, const unsigned char *argmax, float *gx, int n, int d, int h, int w, int c, const int *kernel3,
+                           const int *stride3, const int *pad3, void *stream);
+/* replaces: F.interpolate(x, scale_factor=2) (mode 'nearest') of the FPN top-down path, models/backbone.py:147-153.  x [n,d,h,w,c] ->
+ * y [n,d*fd,h*fh,w*fw,c], factors 1 or 2 per axis; backward sums the children of each input voxel (gather, gx fully written). */
+int mdt_upsample_nearest_forward(const float *x, float *y, int n, int d, int h, int w, int c, int fd, int fh, int fw, void *stream);
+int mdt_upsample_nearest_backward(const float *gy, float *gx, int n, int d, int h, int w, int c, int fd, int fh, int fw, void *stream);
+
+/* ------------------------------------------------------------- loss-side kernels (csrc/loss_ops.cu) ------------------------------------------
+ * Segmentation loss.  replaces: F.softmax(seg_logits, 1) + get_one_hot_encoding + batch_dice (utils/model_utils.py:785-799, 833-858) and
+ * F.cross_entropy(seg_logits, seg[:, 0]) of models/retina_unet.py:395,446-448 (same calls in models/mrcnn.py is n/a; ufrcnn.py uses them too).
+ * logits[b, c, v] = logits + b*strides3[0] + c*strides3[1] + v*strides3[2] (elements; NCDHW: {C*V, V, 1}, channels-last: {V*C, 1, C});
+ * target uint8 [n, voxels]; n_classes <= 8.  sums (device, 3*n_classes + 1 doubles) = per-class intersect, sum p, sum y, then sum(-log p_t) —
+ * saved for the backward; out2 (device) = {dice score (mean over foreground classes, batch pseudo-volume), mean cross-entropy}.
+ * Deterministic (fixed-order fp64 reduction).  backward: grad_out2 (device) = {dL/d dice_score, dL/d ce}; grad_logits has logits' strides. */
+size_t mdt_seg_loss_workspace_bytes(int n_classes);
+int mdt_seg_loss_forward(const float *logits, const long long *strides3, const unsigned char *target, int n, long long voxels, int n_classes,
+                         float false_positive_weight, float smooth, double *sums, float *out2, void *ws, size_t ws_bytes, void *stream);
+int mdt_seg_loss_backward(const float *logits, const long long *strides3, const unsigned char *target, int n, long long voxels, int n_classes,
+                          float false_positive_weight, float smooth, const double *sums, const float *grad_out2, float *grad_logits, void *stream);
+/* Class loss with stochastic hard-example mining.  replaces: compute_class_loss (models/retina_unet.py:126-164) / compute_rpn_class_loss
+ * (models/mrcnn.py:176-213) incl. mutils.shem (utils/model_utils.py:674-691): softmax over all anchors, sort of the negatives' max foreground
+ * probability, randperm sample, two cross-entropies.  logits [n_anchors, n_classes] contiguous fp32, matches int32 (-1 negative, 0 neutral,
+ * > 0 positive class); pos_ids = the first n_pos_list positive anchor ids (int64, ascending; at most k_pos are used); k_pool = size of the
+ * candidate pool (<= 1024, = shem_poolsize * k_pos), k_neg <= k_pool sampled negatives at most; rand_keys [k_pool] uniform [0,1) floats from the
+ * caller's generator (the negative_count = max(1, #positives) pool members with the smallest keys are the sample).
+ * Outputs (device): loss[1] = (CE_pos + CE_neg) / 2; neg_ix [k_neg] int64 = rank of each sampled negative inside the negative subset (-1 pad);
+ * sel_rows / sel_labels / sel_w [k_pos + k_neg] = the rows entering the loss, their labels and weights (for the backward).
+ * backward: grad_logits [n_anchors, n_classes] is zero-filled, then rows += grad_loss * w * (softmax - onehot). */
+size_t mdt_shem_workspace_bytes(int n_anchors, int k_pool);
+int mdt_shem_class_loss_forward(const float *logits, const int *matches, int n_anchors, int n_classes, const long long *pos_ids, int n_pos_list, int k_pos,
+                                int k_pool, int k_neg, int shem_poolsize, const float *rand_keys, float *loss, long long *neg_ix, int *sel_rows,
+                                int *sel_labels, float *sel_w, void *ws, size_t ws_bytes, void *stream);
+int mdt_shem_class_loss_backward(const float *logits, int n_anchors, int n_classes, const int *sel_rows, const int *sel_labels, const float *sel_w,
+                                 int n_sel, const float *grad_loss, float *grad_logits, void *stream);
+
 /* number of kernel launches issued by this library since load (all entry points) — feeds bench.py's gpu_launches */
 unsigned long long mdt_launch_count(void);
 

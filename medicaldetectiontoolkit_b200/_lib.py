@@ -71,6 +71,16 @@ SIGNATURES = {
     "mdt_conv3d_fprop_out": (_I, [ctypes.POINTER(Conv3dDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_upsample221_forward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "mdt_upsample221_backward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "mdt_maxpool3d_forward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _VP]),
+    "mdt_maxpool3d_backward": (_I, [_VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _VP]),
+    "mdt_upsample_nearest_forward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mdt_upsample_nearest_backward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _VP]),
+    "mdt_seg_loss_workspace_bytes": (_SZ, [_I]),
+    "mdt_seg_loss_forward": (_I, [_VP, c_i64p, _VP, _I, _I64, _I, _F, _F, _VP, _VP, _VP, _SZ, _VP]),
+    "mdt_seg_loss_backward": (_I, [_VP, c_i64p, _VP, _I, _I64, _I, _F, _F, _VP, _VP, _VP, _VP]),
+    "mdt_shem_workspace_bytes": (_SZ, [_I, _I]),
+    "mdt_shem_class_loss_forward": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mdt_shem_class_loss_backward": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
 }
 
 

@@ -10,8 +10,10 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 try:
+    from . import _lib as L
     from .conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer, pointwise_eligible
 except ImportError:   # loaded by FILE PATH as the reference does (utils.import_module('bbone', cf.backbone_path), mrcnn.py:842): no parent package
+    from medicaldetectiontoolkit_b200 import _lib as L
     from medicaldetectiontoolkit_b200.conv import Conv3d, Conv2d, _Conv3dFn, no_split_consumer, pointwise_eligible
 
 _CL3 = torch.channels_last_3d
@@ -68,7 +70,6 @@ class _Upsample221(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        from . import _lib as L
         lib = L.load()
         x = x.contiguous(memory_format=_CL3)
         n, c, d, h, w = x.shape
@@ -80,7 +81,6 @@ class _Upsample221(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        from . import _lib as L
         lib = L.load()
         n, c, d, h, w = ctx.shape
         gy = gy.contiguous(memory_format=_CL3)
@@ -88,6 +88,94 @@ class _Upsample221(torch.autograd.Function):
         with torch.cuda.device(gy.device):
             L.check(lib.mdt_upsample221_backward(L.ptr(gy), L.ptr(gx), n, d, h, w, c, L.stream_ptr()))
         return gx
+
+
+def _i3(vals):
+    import ctypes
+    return (ctypes.c_int * 3)(*[int(v) for v in vals])
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    """channels-last max pooling on libmdt_b200 (csrc/resample.cu): forward keeps one arg-max byte per element, backward is a gather"""
+
+    @staticmethod
+    def forward(ctx, x, kernel, stride, pad):
+        lib = L.load()
+        x = x.contiguous(memory_format=_CL3)
+        n, c, d, h, w = x.shape
+        od, oh, ow = [(i + 2 * p - k) // s + 1 for i, k, s, p in zip((d, h, w), kernel, stride, pad)]
+        y = torch.empty((n, c, od, oh, ow), dtype=x.dtype, device=x.device, memory_format=_CL3)
+        arg = torch.empty((n, od, oh, ow, c), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(lib.mdt_maxpool3d_forward(L.ptr(x), L.ptr(y), L.ptr(arg), n, d, h, w, c, _i3(kernel), _i3(stride), _i3(pad), L.stream_ptr()))
+        ctx.save_for_backward(arg)
+        ctx.geom = (n, c, d, h, w, kernel, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        (arg,) = ctx.saved_tensors
+        n, c, d, h, w, kernel, stride, pad = ctx.geom
+        gy = gy.contiguous(memory_format=_CL3)
+        gx = torch.empty((n, c, d, h, w), dtype=gy.dtype, device=gy.device, memory_format=_CL3)
+        with torch.cuda.device(gy.device):
+            L.check(lib.mdt_maxpool3d_backward(L.ptr(gy), L.ptr(arg), L.ptr(gx), n, d, h, w, c, _i3(kernel), _i3(stride), _i3(pad), L.stream_ptr()))
+        return gx, None, None, None
+
+
+class MaxPool(nn.Module):
+    """nn.MaxPool3d(kernel_size=3, stride=(2,2,1), padding=1) / nn.MaxPool2d(3, 2, 1) in front of C2 (models/backbone.py:63-64) on the library's
+    own kernels for CUDA fp32 maps; parameter-free, so the state-dict keys of `C2` are unchanged"""
+
+    def __init__(self, dim, kernel_size, stride, padding):
+        super().__init__()
+        t = lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v,) * dim
+        self.dim = dim
+        self.kernel_size, self.stride, self.padding = t(kernel_size), t(stride), t(padding)
+
+    def forward(self, x):
+        if not (x.is_cuda and x.dtype == torch.float32):
+            pool = F.max_pool3d if self.dim == 3 else F.max_pool2d
+            return pool(x, self.kernel_size, self.stride, self.padding)
+        if self.dim == 3:
+            return _MaxPoolFn.apply(x, self.kernel_size, self.stride, self.padding)
+        y = _MaxPoolFn.apply(x.unsqueeze(2), (1,) + self.kernel_size, (1,) + self.stride, (0,) + self.padding)
+        return y.squeeze(2)
+
+
+class _NearestUp2Fn(torch.autograd.Function):
+    """F.interpolate(x, scale_factor=2) (nearest) of the FPN top-down path (models/backbone.py:147-153) on csrc/resample.cu; backward = child sum"""
+
+    @staticmethod
+    def forward(ctx, x, fd):
+        lib = L.load()
+        x = x.contiguous(memory_format=_CL3)
+        n, c, d, h, w = x.shape
+        y = torch.empty((n, c, d * fd, 2 * h, 2 * w), dtype=x.dtype, device=x.device, memory_format=_CL3)
+        with torch.cuda.device(x.device):
+            L.check(lib.mdt_upsample_nearest_forward(L.ptr(x), L.ptr(y), n, d, h, w, c, fd, 2, 2, L.stream_ptr()))
+        ctx.geom = (n, c, d, h, w, fd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = L.load()
+        n, c, d, h, w, fd = ctx.geom
+        gy = gy.contiguous(memory_format=_CL3)
+        gx = torch.empty((n, c, d, h, w), dtype=gy.dtype, device=gy.device, memory_format=_CL3)
+        with torch.cuda.device(gy.device):
+            L.check(lib.mdt_upsample_nearest_backward(L.ptr(gy), L.ptr(gx), n, d, h, w, c, fd, 2, 2, L.stream_ptr()))
+        return gx, None
+
+
+def nearest_up2(x):
+    """nearest x2 along every spatial axis, own kernels for CUDA fp32 maps (5-D: all three axes, 4-D: both)"""
+    if not (x.is_cuda and x.dtype == torch.float32):
+        return F.interpolate(x, scale_factor=2)
+    if x.dim() == 5:
+        return _NearestUp2Fn.apply(x, 2)
+    return _NearestUp2Fn.apply(x.unsqueeze(2), 1).squeeze(2)
 
 
 class Interpolate(nn.Module):
@@ -134,7 +222,7 @@ class FPN(nn.Module):
             layers += [ResBlock(planes * 4, planes, **blk) for _ in range(1, n)]
             return layers
 
-        pool = nn.MaxPool3d(kernel_size=3, stride=(2, 2, 1), padding=1) if three_d else nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        pool = MaxPool(3, 3, (2, 2, 1), 1) if three_d else MaxPool(2, 3, 2, 1)
         self.C2 = nn.Sequential(pool, *stage(sf, sf, self.n_blocks[0], 1, (sf, self.block_expansion, 1)))
         self.C3 = nn.Sequential(*stage(sfe, sf * 2, self.n_blocks[1], 2, (sfe, 2, 2)))
         self.C4 = nn.Sequential(*stage(sfe * 2, sf * 4, self.n_blocks[2], 2, (sfe * 2, 2, 2)))
@@ -176,7 +264,7 @@ class FPN(nn.Module):
     @staticmethod
     def _lateral(conv_mod, c, top):
         """lateral 1x1 conv + nearest x2 upsampled coarser map, the add fused into the conv epilogue when possible"""
-        up = F.interpolate(top, scale_factor=2)
+        up = nearest_up2(top)
         fused = None
         if isinstance(conv_mod, Conv3d):
             fused = _Conv3dFn.apply(c, conv_mod.weight, conv_mod.bias, _to_cl(up), conv_mod.stride, conv_mod.padding, False, conv_mod.precision,

@@ -453,14 +453,15 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
     auto *mask = reinterpret_cast<unsigned long long *>(ws);
     int rc = launch_mask<DIM>(n, boxes, mask, thresh, /*full=*/0, st);
     if (rc != MDT_OK) return rc;
-    if (scan_variant() == 1) {
+    auto single_cta_scan = [&]() -> int {
         const size_t smem = (size_t)cb * sizeof(unsigned long long);
         if (smem > 200 * 1024) return MDT_EUNSUPPORTED;  // N <= 1.6 M boxes
         static bool attr_set[kMaxDevices] = {};
         if (!ensure_smem_attr(nms_scan_kernel, 200 * 1024, attr_set)) return MDT_EUNSUPPORTED;
         nms_scan_kernel<<<1, kScanThreads, smem, st>>>(n, cb, mask, keep, num_out);
         return launch_status();
-    }
+    };
+    if (scan_variant() == 1) return single_cta_scan();
     auto *remv_g = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(ws) + scan_ctl_offset(n));
     auto *ctl = reinterpret_cast<ScanCtl *>(remv_g + cb);
     cudaError_t e = cudaMemsetAsync(remv_g, 0, (size_t)cb * sizeof(unsigned long long) + sizeof(ScanCtl), st);
@@ -471,10 +472,20 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
     // CTA 0 + workers, one CTA per SM at most (cooperative launch: all co-resident); a ticket starts two chunks ahead of the chunk that
     // issues it, so up to 32 blocks need no worker at all; ~8 bitmap words per worker and ticket at least
     int grid = cb > 2 * kChunkBlocks ? 1 + ceil_div(cb - 2 * kChunkBlocks, 8) : 1;
-    if (grid > num_sms()) grid = num_sms();
+    // co-residency limit of THIS device (MIG / MPS slices and other GPUs have fewer SMs than the first device this process saw)
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nms_scan_grid_kernel, kChunkRows, smem) != cudaSuccess || sms * per_sm < 1) {
+        (void)cudaGetLastError();
+        return single_cta_scan();
+    }
+    if (grid > sms * per_sm) grid = sms * per_sm;
     void *args[] = {&n, &cb, &mask, &remv_g, &ctl, &keep, &num_out};
     e = cudaLaunchCooperativeKernel((const void *)nms_scan_grid_kernel, dim3(grid), dim3(kChunkRows), args, smem, st);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();          // e.g. cudaErrorCooperativeLaunchTooLarge under a reduced SM set: the single-CTA reduction always runs
+        return single_cta_scan();
+    }
     return launch_status();
 }
 

@@ -311,3 +311,41 @@ def batch_dice(pred, y, false_positive_weight=1.0, smooth=1e-6):
     intersect = (pred * y).sum(axes)
     denom = (false_positive_weight * pred + y).sum(axes)
     return torch.mean(((2 * intersect + smooth) / (denom + smooth))[1:])
+
+
+def initialize_weights(net):
+    """cf.weight_init in {'xavier_uniform', 'xavier_normal', 'kaiming_uniform', 'kaiming_normal'} applied to every conv / transposed-conv /
+    linear layer exactly as utils/model_utils.py:695-728 does for nn.Conv{2,3}d, nn.ConvTranspose{2,3}d and nn.Linear (the modules here keep
+    the reference's parameter layouts, so the fan computations and the RNG consumption order are the same)."""
+    import numpy as _np
+    import torch.nn as nn
+    init_type = net.cf.weight_init
+    if init_type is None:
+        return
+    if init_type not in ('xavier_uniform', 'xavier_normal', 'kaiming_uniform', 'kaiming_normal'):
+        raise NotImplementedError("cf.weight_init = %r (the reference silently leaves the default initialisation in that case)" % (init_type,))
+    from .conv import Conv2d, Conv3d
+    kinds = (Conv2d, Conv3d, nn.Conv2d, nn.Conv3d, nn.ConvTranspose2d, nn.ConvTranspose3d, nn.Linear)
+    for m in net.modules():
+        if not (isinstance(m, kinds) or type(m).__name__ == '_Deconv2x'):
+            continue
+        if init_type == 'xavier_uniform':
+            nn.init.xavier_uniform_(m.weight.data)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif init_type == 'xavier_normal':
+            nn.init.xavier_normal_(m.weight.data)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif init_type == 'kaiming_uniform':
+            nn.init.kaiming_uniform_(m.weight.data, mode='fan_out', nonlinearity=net.cf.relu, a=0)
+            if m.bias is not None:
+                _, fan_out = nn.init._calculate_fan_in_and_fan_out(m.weight.data)
+                bound = 1 / _np.sqrt(fan_out)
+                nn.init.uniform_(m.bias, -bound, bound)
+        else:
+            nn.init.kaiming_normal_(m.weight.data, mode='fan_out', nonlinearity=net.cf.relu, a=0)
+            if m.bias is not None:
+                _, fan_out = nn.init._calculate_fan_in_and_fan_out(m.weight.data)
+                bound = 1 / _np.sqrt(fan_out)
+                nn.init.normal_(m.bias, -bound, bound)

@@ -352,6 +352,12 @@ class net(nn.Module):
         self.cf = cf
         self.logger = logger
         self.build()
+        if getattr(cf, 'weight_init', None) is not None:
+            if logger is not None:
+                logger.info("using pytorch weight init of type {}".format(cf.weight_init))
+            mutils.initialize_weights(self)                       # mrcnn.py:819-823
+        elif logger is not None:
+            logger.info("using default pytorch weight init")
 
     def build(self):
         cf = self.cf

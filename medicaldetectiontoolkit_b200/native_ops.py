@@ -257,3 +257,126 @@ class CropAndResize(torch.nn.Module):
 
 class CropAndResize2D(CropAndResize):
     _fn = CropAndResizeFunction2D
+
+
+# ------------------------------------------------------------------------------------------------------------------ loss-side kernels
+def _seg_layout(logits):
+    """(batch, class, voxel) element strides of a [b, c, spatial...] logit map whose spatial axes collapse to one stride; None otherwise"""
+    sp = logits.shape[2:]
+    st = logits.stride()
+    sv = st[-1]
+    run = sv
+    for size, stride in zip(reversed(sp), reversed(st[2:])):
+        if size != 1 and stride != run:
+            return None
+        run *= size
+    return st[0], st[1], sv
+
+
+class _SegLoss(torch.autograd.Function):
+    """(dice score over the batch pseudo-volume, mean voxel cross-entropy) of seg logits vs a uint8 label map, csrc/loss_ops.cu — replaces
+    softmax + one-hot + batch_dice + cross_entropy (retina_unet.py:395,446-448; model_utils.py:785-799,833-858) by one pass each way"""
+
+    @staticmethod
+    def forward(ctx, logits, target, fpw, smooth):
+        L.require_cuda(logits, target)
+        lib = L.load()
+        lay = _seg_layout(logits)
+        if lay is None:
+            logits = logits.contiguous()
+            lay = _seg_layout(logits)
+        n, c = logits.shape[0], logits.shape[1]
+        vox = 1
+        for s in logits.shape[2:]:
+            vox *= s
+        if target.dtype != torch.uint8 or target.numel() != n * vox or not target.is_contiguous():
+            raise L.MdtError("seg_loss: target must be a contiguous uint8 label map with one entry per voxel")
+        dev = logits.device
+        sums = torch.empty(3 * c + 1, dtype=torch.float64, device=dev)
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        ws_bytes = lib.mdt_seg_loss_workspace_bytes(c)
+        if ws_bytes == 0:
+            raise L.MdtError("seg_loss: at most 8 classes")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        strides = L.i64arr(lay)
+        with torch.cuda.device(dev):
+            L.check(lib.mdt_seg_loss_forward(L.ptr(logits), strides, L.ptr(target), n, vox, c, float(fpw), float(smooth), L.ptr(sums), L.ptr(out), L.ptr(ws),
+                                             ws_bytes, L.stream_ptr()))
+        ctx.save_for_backward(logits, target, sums)
+        ctx.meta = (lay, n, vox, c, float(fpw), float(smooth))
+        return out[0], out[1]
+
+    @staticmethod
+    def backward(ctx, g_dice, g_ce):
+        lib = L.load()
+        logits, target, sums = ctx.saved_tensors
+        lay, n, vox, c, fpw, smooth = ctx.meta
+        gout = torch.stack([g_dice.reshape(()), g_ce.reshape(())]).to(torch.float32).contiguous()
+        grad = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float32, device=logits.device)
+        with torch.cuda.device(logits.device):
+            L.check(lib.mdt_seg_loss_backward(L.ptr(logits), L.i64arr(lay), L.ptr(target), n, vox, c, fpw, smooth, L.ptr(sums), L.ptr(gout), L.ptr(grad),
+                                              L.stream_ptr()))
+        return grad, None, None, None
+
+
+def seg_loss(seg_logits, seg_labels_u8, false_positive_weight=1.0, smooth=1e-6):
+    """-> (batch_dice(softmax(seg_logits), one_hot(labels)), cross_entropy(seg_logits, labels)), both differentiable 0-d tensors"""
+    if seg_logits.dtype != torch.float32:
+        raise L.MdtError("seg_loss: logits must be float32")
+    return _SegLoss.apply(seg_logits, seg_labels_u8, false_positive_weight, smooth)
+
+
+SHEM_MAX_POOL = 1024
+
+
+def shem_supported(logits, k_pos, k_pool):
+    return (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2 and 2 <= logits.shape[1] <= 8 and 1 <= k_pos <= SHEM_MAX_POOL
+            and 1 <= k_pool <= SHEM_MAX_POOL)
+
+
+class _ShemClassLoss(torch.autograd.Function):
+    """fused class loss with stochastic hard-example mining (csrc/loss_ops.cu); see retina_unet.compute_class_loss for the semantics"""
+
+    @staticmethod
+    def forward(ctx, logits, matches, pos_ids, rand_keys, k_pos, k_pool, k_neg, poolsize):
+        L.require_cuda(logits, matches, rand_keys)
+        lib = L.load()
+        logits = logits.contiguous()
+        a, c = logits.shape
+        dev = logits.device
+        matches = matches.to(torch.int32).contiguous()
+        pos_ids = pos_ids.to(torch.int64).contiguous()
+        rand_keys = rand_keys.to(torch.float32).contiguous()
+        if rand_keys.numel() != k_pool:
+            raise L.MdtError("shem: rand_keys must hold k_pool entries")
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        neg_ix = torch.empty(k_neg, dtype=torch.int64, device=dev)
+        rows = torch.empty(k_pos + k_neg, dtype=torch.int32, device=dev)
+        labels = torch.empty(k_pos + k_neg, dtype=torch.int32, device=dev)
+        w = torch.empty(k_pos + k_neg, dtype=torch.float32, device=dev)
+        ws_bytes = lib.mdt_shem_workspace_bytes(a, k_pool)
+        ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            L.check(lib.mdt_shem_class_loss_forward(L.ptr(logits), L.ptr(matches), a, c, L.ptr(pos_ids) if pos_ids.numel() else None, int(pos_ids.numel()),
+                                                    k_pos, k_pool, k_neg, poolsize, L.ptr(rand_keys), L.ptr(loss), L.ptr(neg_ix), L.ptr(rows), L.ptr(labels),
+                                                    L.ptr(w), L.ptr(ws), ws_bytes, L.stream_ptr()))
+        ctx.save_for_backward(logits, rows, labels, w)
+        ctx.mark_non_differentiable(neg_ix)
+        return loss[0], neg_ix
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_neg):
+        lib = L.load()
+        logits, rows, labels, w = ctx.saved_tensors
+        a, c = logits.shape
+        grad = torch.empty_like(logits)
+        g = g_loss.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(logits.device):
+            L.check(lib.mdt_shem_class_loss_backward(L.ptr(logits), a, c, L.ptr(rows), L.ptr(labels), L.ptr(w), int(rows.numel()), L.ptr(g), L.ptr(grad),
+                                                     L.stream_ptr()))
+        return grad, None, None, None, None, None, None, None
+
+
+def shem_class_loss(logits, matches, pos_ids, rand_keys, k_pos, k_pool, k_neg, poolsize):
+    """-> (loss 0-d, neg_ix [k_neg] int64 padded with -1)"""
+    return _ShemClassLoss.apply(logits, matches, pos_ids, rand_keys, int(k_pos), int(k_pool), int(k_neg), int(poolsize))

@@ -25,7 +25,24 @@ class FlatGradAllReduce(object):
     def zero_grad(self):
         self.flat.zero_()
 
+    def _check_aliasing(self):
+        """`optimizer.zero_grad()` (set_to_none=True by default) or any `p.grad = None` silently detaches a parameter from the flat buffer; the
+        all-reduce would then average a stale buffer and the replicas diverge.  Re-bind (and carry over) such gradients."""
+        base = self.flat.data_ptr()
+        off = 0
+        for p in self.params:
+            want = base + off * 4
+            if p.grad is None:                                  # released by zero_grad(set_to_none=True) and not produced since: contributes 0
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+                p.grad.zero_()
+            elif p.grad.data_ptr() != want:
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p.grad)
+                p.grad = view
+            off += p.numel()
+
     def all_reduce(self):
+        self._check_aliasing()
         if self.world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
             self.flat.mul_(1.0 / self.world)

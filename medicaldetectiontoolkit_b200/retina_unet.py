@@ -62,6 +62,9 @@ class BBRegressor(_Tower):
 
 
 # ------------------------------------------------------------------------------------------------------------------ losses
+FUSED_LOSSES = True   # False: the formulation in torch ops (kept as the in-repo cross-check of the fused kernels, tests/test_model_gpu.py)
+
+
 def _topk_long(score, k, blk=8192):
     """exact sorted top-k of a long 1-D tensor for small k: per-block top-k (one batched launch) + top-k of the nb*k candidates.  The
     library's multi-block radix select costs ~11 launches (0.4 ms) per call on the 1.35 M anchor scores of cfg2; the top-k overall is a
@@ -99,6 +102,13 @@ def compute_class_loss(anchor_matches, class_pred_logits, shem_poolsize=20, max_
     """
     A = anchor_matches.shape[0]
     dev = class_pred_logits.device
+    if pos_ids is not None and max_pos is not None and FUSED_LOSSES:
+        k_pos = int(min(A, max_pos))
+        k_pool = int(min(A, shem_poolsize * k_pos))
+        if native_ops.shem_supported(class_pred_logits, k_pos, k_pool):
+            # one fused selection + loss (csrc/loss_ops.cu): same pool, same uniform keys, same sample as the formulation below
+            keys = mutils.rand_keys(k_pool, dev, generator)
+            return native_ops.shem_class_loss(class_pred_logits, anchor_matches, pos_ids, keys, k_pos, k_pool, int(min(k_pool, k_pos)), shem_poolsize)
     pos_flag = (anchor_matches > 0)
     n_pos = pos_flag.sum()
     # max_pos is the caller's guarantee on the number of positives (the matching caps it at rpn_train_anchors_per_image // 2); without
@@ -235,8 +245,12 @@ class net(nn.Module):
         self.cf = cf
         self.logger = logger
         self.build()
-        if getattr(cf, 'weight_init', None) is not None and logger is not None:
-            logger.info("weight_init {} requested: using the PyTorch default initialisation of the conv modules".format(cf.weight_init))
+        if getattr(cf, 'weight_init', None) is not None:
+            if logger is not None:
+                logger.info("using pytorch weight init of type {}".format(cf.weight_init))
+            mutils.initialize_weights(self)                       # retina_unet.py:360-364
+        elif logger is not None:
+            logger.info("using default pytorch weight init")
 
     def build(self):
         cf = self.cf
@@ -316,10 +330,16 @@ class net(nn.Module):
         loss = batch_class_loss + batch_bbox_loss
         seg_dice = seg_ce = None
         if self.has_seg_head:
-            seg = self._to_device(batch['seg'], dtype=torch.long)                     # (b, 1, y, x, (z))
-            seg_ohe = F.one_hot(seg[:, 0], cf.num_seg_classes).movedim(-1, 1).float()  # on-device one-hot (reference: numpy, retina_unet.py:395)
-            seg_dice = 1 - batch_dice(F.softmax(seg_logits, dim=1), seg_ohe)
-            seg_ce = F.cross_entropy(seg_logits, seg[:, 0])
+            if FUSED_LOSSES and seg_logits.is_cuda and cf.num_seg_classes <= 8:
+                # one pass over the logits and the uint8 labels each way (csrc/loss_ops.cu); no one-hot / probability volumes
+                seg = self._to_device(batch['seg'], dtype=torch.uint8).contiguous()   # (b, 1, y, x, (z)), 1 byte per voxel over PCIe
+                dice_score, seg_ce = native_ops.seg_loss(seg_logits, seg)
+                seg_dice = 1 - dice_score
+            else:
+                seg = self._to_device(batch['seg'], dtype=torch.long)                     # (b, 1, y, x, (z))
+                seg_ohe = F.one_hot(seg[:, 0], cf.num_seg_classes).movedim(-1, 1).float()  # on-device one-hot (reference: numpy, retina_unet.py:395)
+                seg_dice = 1 - batch_dice(F.softmax(seg_logits, dim=1), seg_ohe)
+                seg_ce = F.cross_entropy(seg_logits, seg[:, 0])
             loss = loss + (seg_dice + seg_ce) / 2
 
         results_dict = get_results(cf, img.shape, detections, seg_logits, box_results_list)

@@ -106,3 +106,30 @@ def test_reference_forward_on_b200_kernels_matches_the_mirror():
         assert det_r.shape == det_o.shape
     finally:
         _teardown(mutils, saved)
+
+
+@pytest.mark.parametrize("model,init", [("retina_unet", "kaiming_normal"), ("mrcnn", "xavier_uniform"), ("mrcnn", "kaiming_uniform")])
+def test_weight_init_equals_the_reference(model, init):
+    """cf.weight_init (utils/model_utils.py:695-728): the UNMODIFIED reference net (stock nn.Conv3d, its own backbone.py) and the mirror, built
+    under the same seed, end up with bit-identical parameters — same module order, same fans, same RNG consumption."""
+    import ref_shims as RS
+    from medicaldetectiontoolkit_b200 import mrcnn as b200_mrcnn
+    from medicaldetectiontoolkit_b200 import retina_unet as b200_ru
+    from medicaldetectiontoolkit_b200.configs import make_cf
+    RS.install_import_shims()
+    cf = make_cf(model, 3, (32, 32, 16))
+    cf.weight_init = init
+    try:
+        with RS.torch04_semantics(cpu=True):
+            ref = RS.load_ref_module(model)
+            torch.manual_seed(5)
+            rnet = ref.net(RS.ref_cf(cf), RS.Logger())
+        torch.manual_seed(5)
+        ours = (b200_ru if model == "retina_unet" else b200_mrcnn).net(cf, None)
+        rsd, osd = rnet.state_dict(), ours.state_dict()
+        assert list(rsd) == list(osd)
+        for k in rsd:
+            assert torch.equal(rsd[k], osd[k]), k
+    finally:
+        for k in [k for k in sys.modules if k == "cuda_functions" or k.startswith("cuda_functions.")]:
+            del sys.modules[k]

@@ -61,3 +61,25 @@ def test_flat_grad_allreduce_gloo_world2():
         assert all(views)                             # .grad tensors are views of the flat buffer (no flatten copies)
         assert torch.all(reduced[off_unused:off_unused + 5] == 0)   # never-used parameter stays zero: static bucket layout
     assert not torch.allclose(out[0][1], out[1][1])   # ranks really had different local gradients
+
+
+def test_flat_grad_rebinds_after_set_to_none():
+    """optimizer.zero_grad() (set_to_none=True) must not silently detach parameters from the flat all-reduce buffer"""
+    import torch
+    from medicaldetectiontoolkit_b200.parallel import FlatGradAllReduce
+    m = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+    red = FlatGradAllReduce(m, world_size=1)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    m(torch.ones(2, 4)).sum().backward()
+    first = red.flat.clone()
+    assert first.abs().sum() > 0
+    opt.zero_grad()                                  # set_to_none=True: every p.grad is gone
+    m[0](torch.ones(2, 4)).sum().backward()          # only the first layer gets a fresh gradient (new tensors, not views of the buffer)
+    red.all_reduce()
+    off = 0
+    for p in m.parameters():
+        assert p.grad.data_ptr() == red.flat.data_ptr() + 4 * off
+        off += p.numel()
+    n0 = sum(p.numel() for p in m[0].parameters())
+    assert torch.equal(red.flat[:n0], torch.cat([p.grad.reshape(-1) for p in m[0].parameters()]))
+    assert red.flat[n0:].abs().sum() == 0            # stale gradients of the untouched layer are not averaged
