@@ -40,6 +40,7 @@ struct TcWgradParams {
     int planes, stages, tmem_cols, slot_cols;
     int y_chunk_bytes, y_plane_bytes, x_plane_bytes, x_buf_bytes, stage_bytes;
     int y_tx_bytes, x_tx_bytes;      // bytes one TMA box delivers
+    int y_stride, x_base, x_stride;  // shared-memory placement: dy of stage s at s * y_stride, x at x_base + s * x_stride
     long long units;                 // NB * OD * OH * segs
     float *partial;                  // [split][group][mtile][128 lanes][512 cols] fp32 accumulator dumps (reduced by wgrad_reduce_kernel)
     int mtiles;
@@ -101,7 +102,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 decode_unit(u, n, od, oh, ow0);
                 const int s = it % p.stages;
                 mbar_wait(&empty[s], ((it / p.stages) & 1) ^ 1);
-                uint8_t *st = smem + (size_t)s * p.stage_bytes;
+                uint8_t *st = smem + (size_t)s * p.y_stride;
                 // which column blocks have their source line inside the image
                 uint32_t bytes = p.planes * p.nmc * p.y_tx_bytes;
                 for (int b = 0; b < ncb; ++b) {
@@ -116,7 +117,7 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                     for (int mc = 0; mc < p.nmc; ++mc)
                         tma_load_5d(st + (size_t)pl * p.y_plane_bytes + (size_t)mc * p.y_chunk_bytes, &tmY, &full[s], (mt * p.nmc + mc) * p.chunky, ow0,
                                     pl, oh, n * p.OD + od);
-                uint8_t *xb = st + (size_t)p.planes * p.y_plane_bytes;
+                uint8_t *xb = smem + p.x_base + (size_t)s * p.x_stride;
                 for (int b = 0; b < ncb; ++b) {
                     int kd, kh, xc;
                     wg_decode_cb(p, cb0 + b, kd, kh, xc);
@@ -143,8 +144,8 @@ conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 const int s = it % p.stages;
                 mbar_wait(&full[s], (it / p.stages) & 1);
                 tc_fence_after();
-                const uint32_t y_hi = smem_u32(smem + (size_t)s * p.stage_bytes);
-                const uint32_t x0 = y_hi + p.planes * p.y_plane_bytes;
+                const uint32_t y_hi = smem_u32(smem + (size_t)s * p.y_stride);
+                const uint32_t x0 = smem_u32(smem + p.x_base + (size_t)s * p.x_stride);
                 // (measured: interleaving the column blocks inside the K loop does not help — the accumulate dependency is not the limiter, the
                 //  single-thread issue rate is — so keep the order with the fewest instructions per MMA: descriptors advance by integer adds)
                 for (int b = 0; b < ncb; ++b) {
@@ -393,8 +394,27 @@ static int conv_tc_wgrad_impl(const ConvGeom &g, const float *x, const float *dy
     // epilogue); make sure that walk stays inside the allocation for the last stage too
     const size_t walk = (size_t)(128 / w.chunky) * w.rows_y * w.swy;
     const size_t tail = walk > (size_t)p.stage_bytes ? walk - p.stage_bytes : 0;
-    const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + tail;
+    size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + tail;
     if (smem > 218 * 1024) return MDT_EUNSUPPORTED;
+    p.y_stride = p.stage_bytes; p.x_base = planes * p.y_plane_bytes; p.x_stride = p.stage_bytes;
+    // placement experiment (tools/mma_major_probe: the cost of an MMA depends on how far apart its two shared-memory operands lie):
+    // MDT_WG_LAYOUT=1 groups the dy buffers of all stages in front of the x buffers, MDT_WG_GAP (KiB) moves the x region further up
+    if (const char *e = getenv("MDT_WG_LAYOUT")) {
+        if (atoi(e) == 1) {
+            const size_t yreg = wg_align((size_t)planes * p.y_plane_bytes), xreg = wg_align((size_t)w.CB * p.x_buf_bytes);
+            size_t gap = getenv("MDT_WG_GAP") ? (size_t)atoi(getenv("MDT_WG_GAP")) * 1024 : 0;
+            auto total = [&](size_t g_) {
+                const size_t a = p.stages * yreg + g_ + p.stages * xreg, b = (p.stages - 1) * yreg + walk;   // the M = 128 walk from the last dy stage
+                return (a > b ? a : b) + 1024;
+            };
+            size_t need = total(gap);
+            if (need > 218 * 1024) { gap = 0; need = total(0); }
+            if (need <= 218 * 1024) {
+                p.y_stride = (int)yreg; p.x_base = (int)(p.stages * yreg + gap); p.x_stride = (int)xreg;
+                smem = need;
+            }
+        }
+    }
     static bool attr[kMaxDevices] = {};
     if (!ensure_smem_attr(conv_tc_wgrad_kernel, 220 * 1024, attr)) return MDT_EDRIVER;
     dim3 grid((unsigned)(w.groups * p.splits), w.mtiles);
