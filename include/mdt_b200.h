@@ -221,6 +221,20 @@ int mdt_shem_class_loss_forward(const float *logits, const int *matches, int n_a
 int mdt_shem_class_loss_backward(const float *logits, int n_anchors, int n_classes, const int *sel_rows, const int *sel_labels, const float *sel_w,
                                  int n_sel, const float *grad_loss, float *grad_logits, void *stream);
 
+/* ------------------------------------------------------------- inference-side consolidation (csrc/consolidate.cu) ----------------------------
+ * replaces: weighted_box_clustering(dets, box_patch_id, thresh, n_ens) of predictor.py:597-706 (numpy loop per patient and class).
+ * dets [n, 2*dim + 3] fp64 rows = (y1, x1, y2, x2, (z1, z2), score, patch-centre factor, number of overlapping patches); patch_id [n] int32 in
+ * [0, n_patches) (the caller maps the reference's patch-id strings to dense ints); order [n] int32 = box indices by descending score.
+ * Outputs (device): keep_scores [<= n], keep_coords [<= n, 2*dim] in cluster order, n_keep[1].  One resident CTA runs the whole greedy loop. */
+size_t mdt_wbc_workspace_bytes(int n, int n_patches);
+int mdt_wbc(const double *dets, const int *patch_id, const int *order, int n, int dim, int n_patches, double thresh, double n_ens, double *keep_scores,
+            double *keep_coords, int *n_keep, void *ws, size_t ws_bytes, void *stream);
+/* replaces: nms_2to3D(dets, thresh) of predictor.py:710-773.  dets [n, 6] fp64 rows = (y1, x1, y2, x2, score, slice id), slice ids in
+ * [0, n_slices); order as above.  Outputs: keep [<= n] int64 indices of the cluster cores, keep_z [<= n, 2] = (z1, z2), n_keep[1]. */
+size_t mdt_nms_2to3d_workspace_bytes(int n, int n_slices);
+int mdt_nms_2to3d(const double *dets, const int *order, int n, double thresh, int n_slices, long long *keep, double *keep_z, int *n_keep, void *ws,
+                  size_t ws_bytes, void *stream);
+
 /* number of kernel launches issued by this library since load (all entry points) — feeds bench.py's gpu_launches */
 unsigned long long mdt_launch_count(void);
 

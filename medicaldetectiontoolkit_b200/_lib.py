@@ -81,6 +81,10 @@ SIGNATURES = {
     "mdt_shem_workspace_bytes": (_SZ, [_I, _I]),
     "mdt_shem_class_loss_forward": (_I, [_VP, _VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "mdt_shem_class_loss_backward": (_I, [_VP, _I, _I, _VP, _VP, _VP, _I, _VP, _VP, _VP]),
+    "mdt_wbc_workspace_bytes": (_SZ, [_I, _I]),
+    "mdt_wbc": (_I, [_VP, _VP, _VP, _I, _I, _I, _D, _D, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "mdt_nms_2to3d_workspace_bytes": (_SZ, [_I, _I]),
+    "mdt_nms_2to3d": (_I, [_VP, _VP, _I, _D, _I, _VP, _VP, _VP, _VP, _SZ, _VP]),
 }
 
 

@@ -1,0 +1,35 @@
+"""CPU side of the consolidation row: the committed golden vectors are self-consistent and — where the reference tree is present
+(build container) — regenerate bit-identically from the reference's unmodified predictor.py."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "consolidate.npz")
+
+
+def test_golden_file_shapes():
+    g = np.load(GOLD)
+    for name in ("wbc3d_a", "wbc3d_b", "wbc2d_a", "wbc3d_big"):
+        dim = 2 if g[name + "__dets"].shape[1] == 7 else 3
+        assert g[name + "__keep_coords"].shape == (g[name + "__keep_scores"].shape[0], 2 * dim)
+        assert np.all(g[name + "__keep_scores"] > 0.01)                             # predictor.py:700 filter
+        assert np.unique(g[name + "__dets"][:, -3]).size == g[name + "__dets"].shape[0]   # unique scores: order is well defined
+    for name in ("merge_a", "merge_b"):
+        assert g[name + "__keep_z"].shape == (g[name + "__keep"].shape[0], 2)
+        assert np.all(g[name + "__keep_z"][:, 1] - g[name + "__keep_z"][:, 0] >= 2)     # z1 = min - 1, z2 = max + 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference tree not present")
+def test_golden_regenerates_from_the_reference(tmp_path):
+    import shutil
+    gold_dir = tmp_path / "golden"
+    shutil.copytree(os.path.join(ROOT, "tests", "golden"), gold_dir, ignore=shutil.ignore_patterns("*.npz", "__pycache__"))
+    subprocess.check_call([sys.executable, str(gold_dir / "make_consolidate_golden.py")], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    a, b = np.load(GOLD), np.load(str(gold_dir / "consolidate.npz"))
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k]), k

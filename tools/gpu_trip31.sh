@@ -2,7 +2,7 @@
 # trip 31: new loss/resample kernels (parity), operand-placement probe, wgrad placement experiment, full GPU suite, bench
 mkdir -p gpurun_out
 timeout 120 tools/bin/mma_major_probe > gpurun_out/mma_major_probe.txt 2>&1; cat gpurun_out/mma_major_probe.txt
-timeout 600 python -m pytest tests/test_loss_ops_gpu.py -m gpu -q --tb=short 2>&1 | grep -v Warning | tail -40 > gpurun_out/pytest_loss_ops.txt; cat gpurun_out/pytest_loss_ops.txt
+timeout 600 python -m pytest tests/test_loss_ops_gpu.py tests/test_consolidate_gpu.py -m gpu -q --tb=short 2>&1 | grep -v Warning | tail -40 > gpurun_out/pytest_loss_ops.txt; cat gpurun_out/pytest_loss_ops.txt
 for lay in 0 1; do for gap in 0 16; do
   echo "== MDT_WG_LAYOUT=$lay MDT_WG_GAP=$gap"; MDT_WG_LAYOUT=$lay MDT_WG_GAP=$gap PASSES=2 timeout 120 python tools/conv_layer_bench.py p0_36 c0_18 c1_k7 head64
 done; done > gpurun_out/wgrad_layout.txt 2>&1; cat gpurun_out/wgrad_layout.txt
