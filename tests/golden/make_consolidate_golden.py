@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Golden vectors for the inference-side consolidation, produced by the REFERENCE's own numpy functions
 (/root/reference/predictor.py:597-706 weighted_box_clustering, :710-773 nms_2to3D) imported unmodified under the import shims.
-Run in the build container:  python tests/golden/make_consolidate_golden.py   ->  tests/golden/consolidate.npz
+Run in the build container:  python tests/golden/make_consolidate_golden.py [out.npz]   ->  tests/golden/consolidate.npz
 Inputs are seeded; scores are unique (argsort()[::-1] leaves the order of ties to numpy's unstable quicksort)."""
 import os
 import sys
@@ -58,7 +58,7 @@ def main():
     cases = [("wbc3d_a", 3, 12, 6, 0.1, 4), ("wbc3d_b", 3, 60, 9, 1e-5, 1), ("wbc2d_a", 2, 25, 7, 0.1, 5), ("wbc3d_single", 3, 1, 1, 0.1, 3),
              ("wbc3d_big", 3, 300, 8, 0.1, 4)]
     for name, dim, nc, per, thresh, n_ens in cases:
-        rs = np.random.RandomState(abs(hash(name)) % (2 ** 31) if False else sum(map(ord, name)))
+        rs = np.random.RandomState(sum(map(ord, name)))
         dets, pids = wbc_case(rs, nc, per, dim)
         ks, kc = ref.weighted_box_clustering(dets.copy(), pids, thresh, n_ens)
         out[name + "__dets"] = dets
@@ -76,7 +76,7 @@ def main():
         out[name + "__keep"] = np.array(keep, dtype=np.int64)
         out[name + "__keep_z"] = np.array(keep_z, dtype=np.float64).reshape(len(keep), 2)
         print(name, dets.shape, "->", len(keep), "cubes")
-    np.savez_compressed(os.path.join(HERE, "consolidate.npz"), **out)
+    np.savez_compressed(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "consolidate.npz"), **out)
 
 
 if __name__ == "__main__":
