@@ -1,8 +1,8 @@
 """Loss-side and resampling kernels (csrc/loss_ops.cu, csrc/resample.cu) against plain PyTorch restatements of the reference formulas
 (floating-point kernels => torch fp64 reference, tolerances written at each check):
 
-  * max pooling k3 / s(2,2,1) / p1 and nearest x2 up-sampling of models/backbone.py:63-64,147-153: forward bit-exact, backward bit-exact
-    (pure selection / sums of at most 8 terms in the same order are not required: compared to 1e-6);
+  * max pooling k3 / s(2,2,1) / p1 and nearest x2 up-sampling of models/backbone.py:63-64,147-153: forward bit-exact, backward
+    up to the order of the fp32 sums (<= 12 terms; ATen itself uses atomics): 1e-5;
   * segmentation loss = batch_dice(softmax, one_hot) + cross_entropy (utils/model_utils.py:833-858, retina_unet.py:446-448): values 1e-6,
     gradient 1e-5 relative to its max;
   * SHEM class loss (retina_unet.py:126-164, model_utils.py:674-691): the fused kernel chain must select the SAME pool and the SAME sample as
@@ -35,7 +35,7 @@ def test_maxpool3d_matches_torch(shape):
     g = torch.randn_like(yr)
     y.backward(g)
     yr.backward(g)
-    assert torch.allclose(x.grad, xr.grad, rtol=0, atol=1e-6)      # sums of <= 12 gradients, order may differ
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-5, atol=1e-5)   # fp32 sums of <= 12 gradients in a different order (ATen: atomics)
     # ties and -inf / NaN follow ATen's update rule (first maximum in (d, h, w) order; NaN propagates)
     t = torch.zeros(1, 4, 6, 6, 4, device=DEV).contiguous(memory_format=CL3).requires_grad_(True)
     tr = t.detach().clone().requires_grad_(True)
@@ -58,7 +58,7 @@ def test_maxpool2d_matches_torch():
     g = torch.randn_like(yr)
     y.backward(g)
     yr.backward(g)
-    assert torch.allclose(x.grad, xr.grad, rtol=0, atol=1e-6)
+    assert torch.allclose(x.grad, xr.grad, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("shape", [(2, 36, 4, 4, 8), (1, 18, 3, 5, 7), (2, 12, 6, 10)])

@@ -30,7 +30,7 @@ def launches(path):
         a[1] += float(r[v].replace(",", "")) / 1e3
     total = sum(a[1] for a in agg.values())
     print("launches %d, total %.0f us (cold-cache, serialised under ncu: compare SHARES)" % (len(rows) - 1, total))
-    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+    for name, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
         print("%-72s %5d launches %10.1f us %5.1f%%" % (name, n, us, 100 * us / total))
 
 
