@@ -263,7 +263,9 @@ int conv_bias_grad(const ConvGeom &g, const float *dy, float *db, cudaStream_t s
     const long long M = (long long)g.n * g.od * g.oh * g.ow;
     cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * g.cout, st);
     if (e != cudaSuccess) return (int)e;
-    long long blocks_ll = ceil_div<long long>(M, 1024);
+    // rows per block: 1024 for the full-resolution maps (one atomic per channel and block), down to 32 for the small deep maps — the wide
+    // (cout > 256) path walks its rows serially per thread and took 113-146 us on 1-4 blocks for 1-5 MB tensors (profiles/r02_ncu_launches.csv)
+    long long blocks_ll = ceil_div<long long>(M, g.cout > 256 ? 32 : (M >= 262144 ? 1024 : 128));
     if (blocks_ll > (long long)num_sms() * 8) blocks_ll = (long long)num_sms() * 8;
     const int blocks = (int)blocks_ll;
     bias_grad_kernel<<<blocks, 256, 0, st>>>(dy, db, M, g.cout, ceil_div<long long>(M, blocks));

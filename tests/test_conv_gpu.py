@@ -234,3 +234,16 @@ def test_epilogue_emits_the_split_planes_of_the_result(cin, cout, k, stride, sp)
     L.check(lib.mdt_conv3d_split(d2, L.ptr(y0), L.ptr(want), L.stream_ptr()))
     torch.cuda.synchronize()
     assert torch.equal(ys, want), (int((ys != want).sum()), ys.numel())
+
+
+@pytest.mark.parametrize("cin,cout,sp", [(72, 288, (8, 8, 32)), (144, 576, (4, 4, 16)), (36, 36, (4, 4, 16)), (18, 72, (32, 32, 64))])
+def test_bias_gradient_of_the_unfused_wgrad(cin, cout, sp):
+    """db = column sums of dy from mdt_conv3d_wgrad (the wide cout > 256 layers of C4/C5 take the row-serial branch of bias_grad_kernel)"""
+    torch.manual_seed(7)
+    x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    gy = torch.randn(2, cout, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    dw, db = C.conv3d_wgrad(x, gy, (cout, cin, 1, 1, 1), (1, 1, 1), (0, 0, 0), True)
+    ref = gy.double().sum((0, 2, 3, 4))
+    assert float((db.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    ref_w = torch.einsum('ncdhw,nkdhw->ck', gy.double(), x.double()).reshape(cout, cin, 1, 1, 1)
+    assert float((dw.double() - ref_w).abs().max() / ref_w.abs().max()) < 1e-4
