@@ -34,12 +34,9 @@ __device__ __forceinline__ float box_volume_a(const float *a, int dim) {
 }
 
 // predicate IoU(a,b) > thresh with `a` the row box (its volume Sa precomputed) and `b` the column box
-// FILTER (experimental, MDT_NMS_FILTER=1): decide `inter / uni > thresh` by two multiplications whenever inter is outside the band
-// thresh * uni * (1 +- 2^-20) and pay the IEEE division only inside it.  With p = rn(thresh * uni): inter > rn(p (1 + 2^-20)) implies
-// inter / uni > thresh (1 + 2^-21), at least 4 ulps above thresh, so the correctly rounded quotient is > thresh; symmetrically below.
-// Bit-identical to the division for thresh in [1e-30, 1], uni in [1, 1e30] (every other case takes the division).  ncu: a warp almost
-// always holds one overlapping lane, so all 32 lanes pay the ~20-instruction division today (45 instructions per pair).
-template <int DIM, bool FILTER = false>
+// (Round 2 measured a two-sided multiply filter in front of the IEEE division — bit-identical keep lists, but 11.09 vs 10.57 ms at 100 k boxes:
+// the extra compares cost more than the divisions they avoid; removed.  profiles/r02_nms_filter_ab.txt)
+template <int DIM>
 __device__ __forceinline__ bool suppresses(const float *a, float Sa, const float *b, float thresh, bool fast_reject) {
     float left = fmaxf(a[0], b[0]), right = fminf(a[2], b[2]);
     float top = fmaxf(a[1], b[1]), bottom = fminf(a[3], b[3]);
@@ -58,11 +55,6 @@ __device__ __forceinline__ bool suppresses(const float *a, float Sa, const float
     if (DIM == 3) sum = __fmaf_rn(__fmul_rn(bh, bw), __fadd_rn(__fsub_rn(b[5], b[4]), 1.f), Sa);
     else          sum = __fmaf_rn(bh, bw, Sa);
     float uni = __fsub_rn(sum, inter);
-    if (FILTER && fast_reject && thresh >= 1e-30f && thresh <= 1.f && uni >= 1.f && uni <= 1e30f) {
-        const float pth = __fmul_rn(thresh, uni);
-        if (inter > __fmul_rn(pth, 1.000001f)) return true;    // 1 + 2^-20
-        if (inter < __fmul_rn(pth, 0.999999f)) return false;   // 1 - 17 * 2^-24
-    }
     return __fdiv_rn(inter, uni) > thresh;
 }
 
@@ -73,16 +65,16 @@ __device__ __forceinline__ bool suppresses(const float *a, float Sa, const float
 // within one iteration.  Heaviest row blocks (most column tiles) are scheduled first.
 constexpr int kMaskGroups = 4;
 
-template <int DIM, bool FILTER = false>
+template <int DIM>
 __device__ __forceinline__ bool suppresses_tile(const float *a, float Sa, const float4 *tile, int i, float thresh, bool fast) {
     float b[6];
     const float4 b0 = tile[(DIM == 3 ? 2 : 1) * i];   // one (3D: two) 128-bit broadcast loads per column box
     b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
     if (DIM == 3) { const float4 b1 = tile[2 * i + 1]; b[4] = b1.x; b[5] = b1.y; } else { b[4] = b[5] = 0.f; }
-    return suppresses<DIM, FILTER>(a, Sa, b, thresh, fast);
+    return suppresses<DIM>(a, Sa, b, thresh, fast);
 }
 
-template <int DIM, bool FILTER = false>
+template <int DIM>
 __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
                                                                     unsigned long long *__restrict__ mask, int col_blocks, int full) {
     constexpr int F = BoxF<DIM>::n;
@@ -119,13 +111,13 @@ __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, flo
                     unsigned int bits = 0;
 #pragma unroll
                     for (int u = 0; u < 16; ++u)
-                        if (suppresses_tile<DIM, FILTER>(a, Sa, tq, u, thresh, fast)) bits |= 1u << u;
+                        if (suppresses_tile<DIM>(a, Sa, tq, u, thresh, fast)) bits |= 1u << u;
                     word |= (unsigned long long)bits << (16 * q);
                 }
             } else {
                 const int start = (row_blk == col_blk) ? t + 1 : 0;   // a box may only suppress LOWER-scored boxes of its own block
                 for (int i = start; i < col_size; ++i)
-                    if (suppresses_tile<DIM, FILTER>(a, Sa, tile[group], i, thresh, fast)) word |= 1ULL << i;
+                    if (suppresses_tile<DIM>(a, Sa, tile[group], i, thresh, fast)) word |= 1ULL << i;
             }
             mask[(size_t)cur * col_blocks + col_blk] = word;
         }
@@ -425,9 +417,7 @@ static int launch_mask(int n, const float *boxes, unsigned long long *mask, floa
     if (n < 0 || (n > 0 && (!boxes || !mask))) return MDT_EINVAL;
     if (n == 0) return MDT_OK;
     const int cb = ceil_div(n, kTile);
-    const char *e = getenv("MDT_NMS_FILTER");   // experimental division filter, see suppresses<>
-    if (e && e[0] == '1') nms_mask_kernel<DIM, true><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
-    else                  nms_mask_kernel<DIM, false><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
+    nms_mask_kernel<DIM><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
     return launch_status();
 }
 
