@@ -74,9 +74,30 @@ __device__ __forceinline__ bool suppresses_tile(const float *a, float Sa, const 
     return suppresses<DIM>(a, Sa, b, thresh, fast);
 }
 
+// y extent [min y1, max y2] of every 64-box tile (one warp per tile).  The mask kernel skips a (row block, column tile) pair whose extents are
+// separated: then rn(min(a.y2, b.y2) - max(a.y1, b.y1)) <= rn(row_hi - col_lo) <= -1 for every pair (rounding is monotone, -1 is exact), so
+// the kernel's own `width = max(rn(rn(right - left) + 1), 0)` is 0, inter is 0 and `inter / uni > thresh` is false for thresh >= 0: the word
+// is written as 0 without touching the boxes.  Callers that translate independent NMS groups apart along y (one launch for all (batch
+// element, class) groups, retina_unet.refine_detections) and order the boxes group by group skip every cross-group tile this way.
+template <int DIM>
+__global__ void __launch_bounds__(256) nms_tile_bounds_kernel(int n, const float *__restrict__ boxes, float2 *__restrict__ bounds, int col_blocks) {
+    constexpr int F = BoxF<DIM>::n;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= col_blocks) return;
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = lane; i < kTile; i += 32) {
+        const int b = tile * kTile + i;
+        if (b < n) { lo = fminf(lo, boxes[(size_t)b * F]); hi = fmaxf(hi, boxes[(size_t)b * F + 2]); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if (lane == 0) bounds[tile] = make_float2(lo, hi);
+}
+
 template <int DIM>
 __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, float thresh, const float *__restrict__ boxes,
-                                                                    unsigned long long *__restrict__ mask, int col_blocks, int full) {
+                                                                    unsigned long long *__restrict__ mask, int col_blocks, int full,
+                                                                    const float2 *__restrict__ bounds) {
     constexpr int F = BoxF<DIM>::n;
     constexpr int V = DIM == 3 ? 2 : 1;   // float4 slots per staged box
     const int row_blk = blockIdx.x;
@@ -91,9 +112,18 @@ __global__ void __launch_bounds__(kTile *kMaskGroups) nms_mask_kernel(int n, flo
     const float Sa = box_volume_a(a, DIM);
     const bool fast = thresh >= 0.f;
     const int c_begin = full ? 0 : row_blk;
+    const bool can_skip = bounds != nullptr && fast;
+    const float2 rbd = can_skip ? bounds[row_blk] : make_float2(0.f, 0.f);
     for (int c0 = c_begin; c0 < col_blocks; c0 += kMaskGroups) {
         const int col_blk = c0 + group;
         const bool live = col_blk < col_blocks;
+        if (can_skip && live && col_blk != row_blk) {       // uniform over the 64 threads of the group: both group barriers are skipped together
+            const float2 cbd = bounds[col_blk];
+            if (__fsub_rn(rbd.y, cbd.x) <= -1.f || __fsub_rn(cbd.y, rbd.x) <= -1.f) {
+                if (row_live) mask[(size_t)cur * col_blocks + col_blk] = 0ULL;
+                continue;
+            }
+        }
         const int col_size = live ? min(n - col_blk * kTile, kTile) : 0;
         if (t < col_size) {   // coordinates only (the score column is not needed), as 16-byte vectors
             const float *src = boxes + (size_t)(col_blk * kTile + t) * F;
@@ -413,11 +443,15 @@ __global__ void __launch_bounds__(kChunkRows, 1) nms_scan_grid_kernel(int n, int
 }
 
 template <int DIM>
-static int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, int full, cudaStream_t st) {
+static int launch_mask(int n, const float *boxes, unsigned long long *mask, float thresh, int full, cudaStream_t st, float2 *bounds = nullptr) {
     if (n < 0 || (n > 0 && (!boxes || !mask))) return MDT_EINVAL;
     if (n == 0) return MDT_OK;
     const int cb = ceil_div(n, kTile);
-    nms_mask_kernel<DIM><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full);
+    if (bounds) {
+        nms_tile_bounds_kernel<DIM><<<ceil_div(cb, 8), 256, 0, st>>>(n, boxes, bounds, cb);
+        if (int rc = launch_status()) return rc;
+    }
+    nms_mask_kernel<DIM><<<cb, kTile * kMaskGroups, 0, st>>>(n, thresh, boxes, mask, cb, full, bounds);
     return launch_status();
 }
 
@@ -441,7 +475,9 @@ static int nms_fused(const float *boxes, int n, float thresh, void *ws, size_t w
     if (ws_bytes < mdt_nms_workspace_bytes(n)) return MDT_EWORKSPACE;
     int cb = ceil_div(n, kTile);
     auto *mask = reinterpret_cast<unsigned long long *>(ws);
-    int rc = launch_mask<DIM>(n, boxes, mask, thresh, /*full=*/0, st);
+    // tile extents live behind the scan's control block (see mdt_nms_workspace_bytes)
+    float2 *bounds = reinterpret_cast<float2 *>(reinterpret_cast<char *>(ws) + scan_ctl_offset(n) + (size_t)cb * sizeof(unsigned long long) + sizeof(ScanCtl));
+    int rc = launch_mask<DIM>(n, boxes, mask, thresh, /*full=*/0, st, bounds);
     if (rc != MDT_OK) return rc;
     auto single_cta_scan = [&]() -> int {
         const size_t smem = (size_t)cb * sizeof(unsigned long long);
@@ -485,8 +521,8 @@ extern "C" {
 
 size_t mdt_nms_workspace_bytes(int boxes_num) {
     if (boxes_num <= 0) return 0;
-    size_t cb = mdt::ceil_div(boxes_num, mdt::kTile);   // mask [n][cb] + the grid scan's bitmap [cb] and control block
-    return (size_t)boxes_num * cb * sizeof(unsigned long long) + cb * sizeof(unsigned long long) + sizeof(mdt::ScanCtl);
+    size_t cb = mdt::ceil_div(boxes_num, mdt::kTile);   // mask [n][cb] + the grid scan's bitmap [cb] and control block + tile extents [cb]
+    return (size_t)boxes_num * cb * sizeof(unsigned long long) + cb * sizeof(unsigned long long) + sizeof(mdt::ScanCtl) + cb * sizeof(float2);
 }
 
 int mdt_nms_mask_3d(int n, const float *boxes, unsigned long long *mask, float thresh, void *stream) {

@@ -191,12 +191,18 @@ def refine_detections(anchors, probs, deltas, batch_ixs, cf):
     shifted = rois.clone()
     shifted[:, 0] += offs
     shifted[:, 2] += offs
-    dets = torch.cat((shifted, scores.unsqueeze(1)), dim=1).contiguous()  # already sorted by descending score
-    keep_pad, num = native_ops.nms_sorted(dets, cf.detection_nms_threshold, dim)
-    kept = torch.zeros(k, dtype=torch.bool, device=probs.device)
+    dets = torch.cat((shifted, scores.unsqueeze(1)), dim=1)               # already sorted by descending score
+    # group-major order (stable: descending score inside every group): greedy NMS of disjoint groups is the union of the per-group runs, and
+    # the mask kernel skips every 64x64 tile whose boxes lie in different y bands (csrc/nms.cu: nms_tile_bounds_kernel) - 3/4 of the pair tests
+    # with 2 elements x 2 classes
+    order_g = torch.sort(b_ix * n_groups_cls + class_ids, stable=True)[1]
+    keep_pad, num = native_ops.nms_sorted(dets[order_g].contiguous(), cf.detection_nms_threshold, dim)
+    kept_g = torch.zeros(k, dtype=torch.bool, device=probs.device)
     pos = torch.arange(k, device=probs.device)
     valid = pos < num.to(torch.long)
-    kept[keep_pad.clamp(0, k - 1)[valid]] = True
+    kept_g[keep_pad.clamp(0, k - 1)[valid]] = True
+    kept = torch.empty_like(kept_g)
+    kept[order_g] = kept_g                                                # back to descending-score positions
     # top model_max_instances_per_batch_element per element, in score order
     n_b = int(batch_ixs.max().item()) + 1 if batch_ixs.numel() else 1
     onehot = (b_ix.unsqueeze(0) == torch.arange(n_b, device=probs.device).unsqueeze(1)) & kept.unsqueeze(0)   # [n_b, k]: scan along the contiguous dim

@@ -31,8 +31,8 @@ def test_load_and_host_only_calls():
     assert lib.mdt_version() >= 100
     assert lib.mdt_error_string(0) == b"success"
     assert b"workspace" in lib.mdt_error_string(-2)
-    # 1.25 GB mask at cfg4, + the grid scan's suppression bitmap (1563 words) and 32-byte control block
-    assert lib.mdt_nms_workspace_bytes(100000) == 100000 * 1563 * 8 + 1563 * 8 + 32
+    # 1.25 GB mask at cfg4, + the grid scan's suppression bitmap (1563 words), 32-byte control block, 1563 tile extents
+    assert lib.mdt_nms_workspace_bytes(100000) == 100000 * 1563 * 8 + 1563 * 8 + 32 + 1563 * 8
     assert lib.mdt_nms_workspace_bytes(0) == 0
     assert lib.mdt_anchor_match_workspace_bytes(8) >= 8 * 12
 

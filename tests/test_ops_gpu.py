@@ -262,3 +262,22 @@ def test_nms_at_the_exact_threshold():
         assert k == O.nms(lat, thr, 3).tolist(), thr
         kept.append(len(k))
     assert kept[0] == n and kept[1] == n // 2 and kept[2] == n          # IoU == thr keeps both boxes; one ulp below suppresses every second box
+
+
+@pytest.mark.parametrize("dim,thr", [(3, 1e-5), (3, 0.5), (2, 0.3)])
+def test_nms_skips_separated_tiles_bit_exactly(dim, thr):
+    """boxes of independent groups translated apart along y and ordered group by group (what retina_unet.refine_detections feeds): the mask
+    kernel skips (row block, column tile) pairs with separated y extents — the keep list must still be the greedy oracle's, including tiles
+    that straddle a group boundary, touching bands (gap of exactly one pixel = IoU 0) and a ragged last tile"""
+    parts = []
+    for g, n in enumerate((3000, 1777, 64, 2500)):
+        b = O.synth_boxes(n, dim, seed=40 + g, rounded=True)
+        b = b[np.argsort(-b[:, -1], kind="stable")]
+        b[:, 0] += 129.0 * g                                  # extent 128 + 1: neighbouring bands touch without overlapping
+        b[:, 2] += 129.0 * g
+        parts.append(b)
+    boxes = np.concatenate(parts).astype(np.float32)
+    assert _keep(boxes, thr, dim).tolist() == O.nms(boxes, thr, dim).tolist()
+    # negative threshold: disjoint pairs DO suppress (0 > thr), so nothing may be skipped
+    small = boxes[::37].copy()
+    assert _keep(small, -1.0, dim).tolist() == O.nms(small, -1.0, dim).tolist()
