@@ -213,9 +213,10 @@ def refine_detections(anchors, probs, deltas, batch_ixs, cf):
     return torch.cat((rois[sel], b_ix[sel].unsqueeze(1).float(), class_ids[sel].unsqueeze(1).float(), scores[sel].unsqueeze(1)), dim=1)
 
 
-def get_results(cf, img_shape, detections, seg_logits, box_results_list=None):
-    """results_dict {'boxes': per-element lists of box dicts, 'seg_preds': uint8 label map} — retina_unet.py:275-333"""
-    det = detections.detach().cpu().numpy()
+def get_results(cf, img_shape, detections, seg_logits, box_results_list=None, host=None):
+    """results_dict {'boxes': per-element lists of box dicts, 'seg_preds': uint8 label map} — retina_unet.py:275-333.
+    host: optional (detections, seg_preds) numpy arrays already copied to the host (train_forward batches its device->host copies)"""
+    det = detections.detach().cpu().numpy() if host is None else host[0]
     dim = cf.dim
     if box_results_list is None:
         box_results_list = [[] for _ in range(img_shape[0])]
@@ -235,6 +236,8 @@ def get_results(cf, img_shape, detections, seg_logits, box_results_list=None):
     results = {'boxes': box_results_list}
     if seg_logits is None:
         results['seg_preds'] = np.zeros(img_shape)[:, 0][:, np.newaxis]
+    elif host is not None:
+        results['seg_preds'] = host[1]
     else:
         results['seg_preds'] = seg_logits.detach().argmax(1, keepdim=True).to(torch.uint8).cpu().numpy()  # argmax(softmax) == argmax(logits)
     return results
@@ -276,6 +279,11 @@ class net(nn.Module):
     # -------------------------------------------------------------------------------------------------------------- forward
     def forward(self, img):
         """img (b, c, y, x, (z)) -> detections, class_logits (b, n_anchors, n_cls), bb_outputs (b, n_anchors, 2*dim), seg_logits"""
+        class_logits, bb_outputs, seg_logits = self._forward_logits(img)
+        return self._detect(class_logits, bb_outputs), class_logits, bb_outputs, seg_logits
+
+    def _forward_logits(self, img):
+        """the differentiable part of forward(): backbone + heads"""
         fpn_outs = self.Fpn(img)
         if self.has_seg_head:
             seg_logits = self.final_conv(fpn_outs[0])
@@ -286,12 +294,33 @@ class net(nn.Module):
         fmaps = [fpn_outs[i + first] for i in self.cf.pyramid_levels]
         class_logits = torch.cat([self.Classifier(p)[0] for p in fmaps], dim=1)
         bb_outputs = torch.cat([self.BBRegressor(p)[0] for p in fmaps], dim=1)
+        return class_logits, bb_outputs, seg_logits
+
+    def _detect(self, class_logits, bb_outputs):
+        """softmax + refine_detections (ends in the one host sync of the forward: a variable-length result)"""
         b, a = class_logits.shape[0], class_logits.shape[1]
         with torch.no_grad():
-            batch_ixs = torch.arange(b, device=img.device).unsqueeze(1).repeat(1, a).view(-1)
+            batch_ixs = torch.arange(b, device=class_logits.device).unsqueeze(1).repeat(1, a).view(-1)
             flat_softmax = F.softmax(class_logits.detach().view(-1, class_logits.shape[-1]), 1)
-            detections = refine_detections(self.anchors, flat_softmax, bb_outputs.detach().view(-1, bb_outputs.shape[-1]), batch_ixs, self.cf)
-        return detections, class_logits, bb_outputs, seg_logits
+            return refine_detections(self.anchors, flat_softmax, bb_outputs.detach().view(-1, bb_outputs.shape[-1]), batch_ixs, self.cf)
+
+    def _to_host(self, tensors):
+        """device tensors -> numpy through cached pinned staging buffers: all copies are queued, then ONE synchronisation"""
+        if not hasattr(self, '_pin'):
+            self._pin = {}
+        outs = []
+        for i, t in enumerate(tensors):
+            t = t.detach().contiguous()
+            key = (i, tuple(t.shape), t.dtype)
+            buf = self._pin.get(key)
+            if buf is None:
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
+                self._pin[key] = buf
+            buf.copy_(t, non_blocking=True)
+            outs.append(buf)
+        if tensors and tensors[0].is_cuda:
+            torch.cuda.current_stream(tensors[0].device).synchronize()
+        return [o.numpy().copy() for o in outs]
 
     def _to_device(self, arr, dtype=torch.float32):
         """host batch array -> device through pinned memory (non_blocking H2D)"""
@@ -305,28 +334,41 @@ class net(nn.Module):
 
     def train_forward(self, batch, **kwargs):
         """batch: {'data', 'seg', 'bb_target', 'roi_labels', ...} numpy -> results_dict with 'torch_loss', 'boxes', 'seg_preds',
-        'monitor_values', 'logger_string' (retina_unet.py:381-456)."""
+        'monitor_values', 'logger_string' (retina_unet.py:381-456).
+
+        Order of work (results are the reference's; the ORDER keeps the GPU queue full): the anchor matching needs only the GT boxes, so it
+        (and its host synchronisation) runs first; backbone, heads and all losses are then queued without a sync; the detections for the
+        monitoring output (NMS, variable-length result) and every device->host copy come last and share one synchronisation."""
         cf = self.cf
         gt_class_ids = batch['roi_labels']
         gt_boxes = batch['bb_target']
         img = self._to_device(batch['data'])
         n_b = img.shape[0]
+        dev = img.device
         box_results_list = [[] for _ in range(n_b)]
-        detections, class_logits, pred_deltas, seg_logits = self.forward(img)
+        seg = None
+        if self.has_seg_head:
+            fused_seg = FUSED_LOSSES and img.is_cuda and cf.num_seg_classes <= 8
+            seg = self._to_device(batch['seg'], dtype=torch.uint8 if fused_seg else torch.long)   # (b, 1, y, x, (z)); uint8: 1 byte per voxel over PCIe
+
+        matched = []
+        for b in range(n_b):
+            if len(gt_boxes[b]) > 0:
+                for ix in range(len(gt_boxes[b])):
+                    box_results_list[b].append({'box_coords': batch['bb_target'][b][ix], 'box_label': batch['roi_labels'][b][ix], 'box_type': 'gt'})
+                matched.append(mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], gt_class_ids[b], return_pos=True))
+            else:
+                matched.append((torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=dev),
+                                torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=dev),
+                                torch.zeros(0, dtype=torch.long, device=dev)))
+
+        class_logits, pred_deltas, seg_logits = self._forward_logits(img)
 
         max_pos = max(1, cf.rpn_train_anchors_per_image // 2)
         batch_class_loss = img.new_zeros(1)
         batch_bbox_loss = img.new_zeros(1)
         monitor = []
-        for b in range(n_b):
-            if len(gt_boxes[b]) > 0:
-                for ix in range(len(gt_boxes[b])):
-                    box_results_list[b].append({'box_coords': batch['bb_target'][b][ix], 'box_label': batch['roi_labels'][b][ix], 'box_type': 'gt'})
-                match, target_deltas, pos_ids = mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], gt_class_ids[b], return_pos=True)
-            else:
-                match = torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device)
-                target_deltas = torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device)
-                pos_ids = torch.zeros(0, dtype=torch.long, device=img.device)
+        for b, (match, target_deltas, pos_ids) in enumerate(matched):
             class_loss, neg_ix = compute_class_loss(match, class_logits[b], max_pos=max_pos, pos_ids=pos_ids)
             bbox_loss = compute_bbox_loss(target_deltas, pred_deltas[b], match, max_pos=max_pos, pos_ids=pos_ids)
             batch_class_loss = batch_class_loss + class_loss / n_b
@@ -336,28 +378,35 @@ class net(nn.Module):
         loss = batch_class_loss + batch_bbox_loss
         seg_dice = seg_ce = None
         if self.has_seg_head:
-            if FUSED_LOSSES and seg_logits.is_cuda and cf.num_seg_classes <= 8:
+            if fused_seg:
                 # one pass over the logits and the uint8 labels each way (csrc/loss_ops.cu); no one-hot / probability volumes
-                seg = self._to_device(batch['seg'], dtype=torch.uint8).contiguous()   # (b, 1, y, x, (z)), 1 byte per voxel over PCIe
-                dice_score, seg_ce = native_ops.seg_loss(seg_logits, seg)
+                dice_score, seg_ce = native_ops.seg_loss(seg_logits, seg.contiguous())
                 seg_dice = 1 - dice_score
             else:
-                seg = self._to_device(batch['seg'], dtype=torch.long)                     # (b, 1, y, x, (z))
                 seg_ohe = F.one_hot(seg[:, 0], cf.num_seg_classes).movedim(-1, 1).float()  # on-device one-hot (reference: numpy, retina_unet.py:395)
                 seg_dice = 1 - batch_dice(F.softmax(seg_logits, dim=1), seg_ohe)
                 seg_ce = F.cross_entropy(seg_logits, seg[:, 0])
             loss = loss + (seg_dice + seg_ce) / 2
 
-        results_dict = get_results(cf, img.shape, detections, seg_logits, box_results_list)
+        detections = self._detect(class_logits, pred_deltas)
+        vals = torch.stack([loss.detach().reshape(()), batch_class_loss.detach().reshape(()), batch_bbox_loss.detach().reshape(())]
+                           + ([seg_dice.detach().reshape(()), seg_ce.detach().reshape(())] if self.has_seg_head else []))
+        to_host = [detections, vals]
+        if self.has_seg_head:
+            seg_pred = seg_logits.detach().argmax(1, keepdim=True).to(torch.uint8)        # argmax(softmax) == argmax(logits)
+            # "mean pix. pr." of the logger string, reduced on the device (np.mean over the 4 M-voxel label map costs ms of host time per step)
+            vals = torch.cat((vals, (seg_pred.sum(dtype=torch.float64) / seg_pred.numel()).to(vals.dtype).reshape(1)))
+            to_host = [detections, vals, seg_pred]
+        host = self._to_host(to_host)
+        results_dict = get_results(cf, img.shape, detections, seg_logits, box_results_list, host=(host[0], host[2] if self.has_seg_head else None))
         if kwargs.get('monitor_anchors', True):
             self._append_anchor_boxes(results_dict['boxes'], monitor, img.shape[2:])
         results_dict['torch_loss'] = loss
-        vals = torch.stack([loss.detach().reshape(()), batch_class_loss.detach().reshape(()), batch_bbox_loss.detach().reshape(())]
-                           + ([seg_dice.detach().reshape(()), seg_ce.detach().reshape(())] if self.has_seg_head else [])).cpu().tolist()
+        vals = host[1].tolist()
         results_dict['monitor_values'] = {'loss': vals[0], 'class_loss': vals[1]}
         if self.has_seg_head:
             results_dict['logger_string'] = "loss: {0:.2f}, class: {1:.2f}, bbox: {2:.2f}, seg dice: {3:.3f}, seg ce: {4:.3f}, mean pix. pr.: {5:.5f}" \
-                .format(vals[0], vals[1], vals[2], vals[3], vals[4], np.mean(results_dict['seg_preds']))
+                .format(vals[0], vals[1], vals[2], vals[3], vals[4], vals[5])
         else:
             results_dict['logger_string'] = "loss: {0:.2f}, class: {1:.2f}, bbox: {2:.2f}".format(vals[0], vals[1], vals[2])
         return results_dict
