@@ -435,6 +435,17 @@ class net(nn.Module):
         img = self._to_device(batch['data'])
         n_b = img.shape[0]
         box_results_list = [[] for _ in range(n_b)]
+        # the RPN matching needs only the GT boxes: run it (and its host synchronisation) before the network is queued
+        matched = []
+        for b in range(n_b):
+            if len(gt_boxes[b]) > 0:
+                for ix in range(len(gt_boxes[b])):
+                    box_results_list[b].append({'box_coords': gt_boxes[b][ix], 'box_label': gt_class_ids[b][ix], 'box_type': 'gt'})
+                matched.append(mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], return_pos=True))   # class-agnostic
+            else:
+                matched.append((torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device),
+                                torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device),
+                                torch.zeros(0, dtype=torch.long, device=img.device)))
         rpn_class_logits, rpn_pred_deltas, proposal_boxes, detections, detection_masks = self.forward(img)
         logits, pred_deltas, pred_mask, t_cls, t_deltas, t_mask, sample_proposals = self.loss_samples_forward(gt_class_ids, gt_boxes, gt_masks)
 
@@ -442,15 +453,7 @@ class net(nn.Module):
         rpn_class_loss = img.new_zeros(1)
         rpn_bbox_loss = img.new_zeros(1)
         monitor = []
-        for b in range(n_b):
-            if len(gt_boxes[b]) > 0:
-                for ix in range(len(gt_boxes[b])):
-                    box_results_list[b].append({'box_coords': gt_boxes[b][ix], 'box_label': gt_class_ids[b][ix], 'box_type': 'gt'})
-                rpn_match, rpn_target_deltas, pos_ids = mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], return_pos=True)   # class-agnostic
-            else:
-                rpn_match = torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=img.device)
-                rpn_target_deltas = torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=img.device)
-                pos_ids = torch.zeros(0, dtype=torch.long, device=img.device)
+        for b, (rpn_match, rpn_target_deltas, pos_ids) in enumerate(matched):
             cl, neg_ix = compute_rpn_class_loss(rpn_match, rpn_class_logits[b], cf.shem_poolsize, max_pos=max_pos, pos_ids=pos_ids)
             monitor.append((rpn_match, neg_ix))
             rpn_class_loss = rpn_class_loss + cl / n_b
