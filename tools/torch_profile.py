@@ -36,32 +36,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
 
-# ---- where does the GPU idle?  gaps between consecutive device activities (kernels + memcpys) of the profiled step, largest first
-try:
-    from torch.autograd import DeviceType
-    dev_evts = [e for e in prof.events() if e.device_type == DeviceType.CUDA]
-    dev_evts.sort(key=lambda e: e.time_range.start)
-    gaps, busy_end, t0 = [], None, None
-    for e in dev_evts:
-        s, t = e.time_range.start, e.time_range.end
-        if busy_end is None:
-            busy_end, t0 = t, s
-            prev = e
-            continue
-        if s > busy_end:
-            gaps.append((s - busy_end, prev.name[:60], e.name[:60], busy_end - t0))
-        if t > busy_end:
-            busy_end, prev = t, e
-    total_gap = sum(g[0] for g in gaps)
-    print("\ndevice timeline: span %.2f ms, idle %.2f ms in %d gaps (> 20 us: %.2f ms)" % ((busy_end - t0) / 1e3, total_gap / 1e3, len(gaps),
-                                                                                         sum(g[0] for g in gaps if g[0] > 20) / 1e3))
-    print("largest gaps: us | at ms | after kernel -> before kernel")
-    for g in sorted(gaps, reverse=True)[:25]:
-        print("%8.1f | %7.2f | %s -> %s" % (g[0], g[3] / 1e3, g[1], g[2]))
-    # idle time per millisecond bucket of the step
-    buckets = {}
-    for g in gaps:
-        buckets[int(g[3] // 2000)] = buckets.get(int(g[3] // 2000), 0.0) + g[0]
-    print("idle us per 2-ms bucket of the step:", " ".join("%d:%.0f" % (k * 2, v) for k, v in sorted(buckets.items())))
-except Exception as ex:   # the event API differs between torch versions; the table above is the primary output
-    print("gap analysis unavailable:", ex)
+# (sum of "Self CUDA" vs the step time from bench.py gives the GPU idle share; a per-gap analysis over prof.events() took > 5 min here - dropped)
