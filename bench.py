@@ -167,6 +167,7 @@ def make_roofline(step_flops, conv_ms, n_conv_calls, ms_step, dom, peak_tf, peak
 def capture_logits_graph(net, batch, lib, eager_logits, reducer):
     """torch.cuda.make_graphed_callables over net._forward_logits (backbone + heads): one graph for the forward, one for the backward.  Returns
     {"enabled", "kernels_per_step", ...}; on success net._forward_logits is the graphed callable."""
+    import torch
     info = {"enabled": False, "kernels_per_step": 0}
 
     class _Logits(torch.nn.Module):
