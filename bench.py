@@ -227,7 +227,9 @@ def main():
     ap.add_argument("--precision", type=int, default=0, help="0 = fp32-faithful conv (default, parity mode); 1 = single-pass bf16")
     ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 force SIMT conv, 2 force tcgen05 conv")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graphs", action="store_true", help="do not capture backbone + heads (forward and backward) in CUDA graphs")
+    ap.add_argument("--graphs", action="store_true",
+                    help="capture backbone + heads (forward and backward) in CUDA graphs; measured SLOWER than eager launches on this step "
+                         "(53.9 vs 51.8 ms: the conv part is not launch-bound, the replay adds node-to-node latency), hence opt-in")
     ap.add_argument("--model", default="retina_unet", choices=["retina_unet", "mrcnn"],
                     help="retina_unet = BASELINE configs[1] (the metric's config); mrcnn = configs[2]: 3D Mask R-CNN, 512 proposals, RoIAlign 7x7x3")
     args = ap.parse_args()
@@ -317,12 +319,11 @@ def main():
     for h in hooks:
         h.remove()
 
-    # --- CUDA graphs for the static part of the step: backbone + heads, forward and backward (the ~40 small deep layers are launch-bound from
-    # Python: ~3.5 ms of GPU idle per step without graphs).  Matching, losses, NMS, Adam and the all-reduce stay eager.  Falls back to eager
-    # execution if capture fails or the graphed results differ from the eager ones.
+    # --- optional CUDA graphs for the static part of the step: backbone + heads, forward and backward (~900 kernel nodes).  Matching, losses,
+    # NMS, Adam and the all-reduce stay eager.  Falls back to eager execution if capture fails or the graphed results differ from the eager ones.
     graph = {"enabled": False, "kernels_per_step": 0}
     eager_logits = getattr(net, "_forward_logits", None)
-    if not args.no_graphs and not is_mrcnn and eager_logits is not None:
+    if args.graphs and not is_mrcnn and eager_logits is not None:
         graph = capture_logits_graph(net, dev_batches[0], lib, eager_logits, reducer)
         if world > 1:   # all ranks must take the same path (the step's collective count does not depend on it, but keep the replicas identical)
             flag = torch.tensor([1.0 if graph["enabled"] else 0.0], device=dev)

@@ -10,6 +10,8 @@ results_dict keys), re-designed so that a training step never leaves the GPU:
   refine_detections                    :194-271                 top-k instead of a 5.4 M-element sort; ONE batched multi-class NMS launch
   nms_3D per (batch, class) + D2H mask pth_nms.py / nms_cuda.c  csrc/nms.cu bitmask + on-device reduction
 """
+import contextlib
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -351,16 +353,27 @@ class net(nn.Module):
             fused_seg = FUSED_LOSSES and img.is_cuda and cf.num_seg_classes <= 8
             seg = self._to_device(batch['seg'], dtype=torch.uint8 if fused_seg else torch.long)   # (b, 1, y, x, (z)); uint8: 1 byte per voxel over PCIe
 
+        # The matching synchronises with the host (exact-length positive lists, numpy sub-sampling).  On a side stream those waits cover only the
+        # matching kernels, so the host is not held up by — and the GPU not drained of — the previous step's backward pass still in flight.
+        main_stream = torch.cuda.current_stream(dev) if img.is_cuda else None
+        if main_stream is not None and getattr(self, '_match_stream', None) is None:
+            self._match_stream = torch.cuda.Stream(device=dev)
         matched = []
-        for b in range(n_b):
-            if len(gt_boxes[b]) > 0:
-                for ix in range(len(gt_boxes[b])):
-                    box_results_list[b].append({'box_coords': batch['bb_target'][b][ix], 'box_label': batch['roi_labels'][b][ix], 'box_type': 'gt'})
-                matched.append(mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], gt_class_ids[b], return_pos=True))
-            else:
-                matched.append((torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=dev),
-                                torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=dev),
-                                torch.zeros(0, dtype=torch.long, device=dev)))
+        with (torch.cuda.stream(self._match_stream) if main_stream is not None else contextlib.nullcontext()):
+            for b in range(n_b):
+                if len(gt_boxes[b]) > 0:
+                    for ix in range(len(gt_boxes[b])):
+                        box_results_list[b].append({'box_coords': batch['bb_target'][b][ix], 'box_label': batch['roi_labels'][b][ix], 'box_type': 'gt'})
+                    matched.append(mutils.gt_anchor_matching_device(cf, self.anchors_f64, gt_boxes[b], gt_class_ids[b], return_pos=True))
+                else:
+                    matched.append((torch.full((self.anchors.shape[0],), -1, dtype=torch.int32, device=dev),
+                                    torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=dev),
+                                    torch.zeros(0, dtype=torch.long, device=dev)))
+        if main_stream is not None:
+            main_stream.wait_stream(self._match_stream)        # the losses (main stream) consume the matching's tensors
+            for tup in matched:
+                for t in tup:
+                    t.record_stream(main_stream)
 
         class_logits, pred_deltas, seg_logits = self._forward_logits(img)
 
