@@ -18,6 +18,10 @@ TOL = 1e-4
 # (cin, cout, k, stride, pad, spatial)
 SHAPES = [
     (1, 18, 3, 1, 1, (12, 10, 16)),            # C0 first conv (Cin = 1)
+    (1, 18, 3, 1, 1, (3, 5, 128)),             # stem at the full line length; 30 lines = 7.5 groups of the 4-line wgrad kernel
+    (1, 24, 3, 1, 1, (3, 3, 20)),              # stem with 24 output channels (the 32-wide weight padding of the specialised fprop)
+    (1, 7, 3, 1, 1, (2, 3, 9)),                # odd channel count: partial co tiles in the stem wgrad
+    (2, 18, 3, 1, 1, (4, 4, 16)),              # Cin = 2: the generic stem kernels
     (18, 18, 3, 1, 1, (8, 8, 32)),             # C0 second conv / ResBlock conv2
     (18, 18, 7, (2, 2, 1), 3, (16, 16, 12)),   # C1 k7 s(2,2,1)
     (18, 72, 1, 1, 0, (6, 6, 8)),              # bottleneck expand / downsample
