@@ -15,6 +15,7 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 ncu -i gpurun_out/ops.ncu-rep --page raw --csv > gpurun_out/ops_raw.csv 2>/dev/null; wc -c gpurun_out/ops_raw.csv
 python tools/ncu_summary.py ops gpurun_out/ops_raw.csv > gpurun_out/ops_summary.txt 2>&1; head -50 gpurun_out/ops_summary.txt
 [ "$(stat -c %s gpurun_out/ops.ncu-rep 2>/dev/null || echo 0)" -gt 30000000 ] && rm -f gpurun_out/ops.ncu-rep   # gpurun_out is capped at 64 MiB
+timeout 300 python tools/conv_profile.py > gpurun_out/conv_profile.txt 2>&1; head -12 gpurun_out/conv_profile.txt
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --model mrcnn --steps 20 --warmup 5 > gpurun_out/bench_mrcnn.json 2> gpurun_out/bench_mrcnn.err; cut -c1-300 gpurun_out/bench_mrcnn.json
 MDT_REF_BUDGET_S=70 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-300 gpurun_out/bench_ref.json
