@@ -245,6 +245,18 @@ def get_results(cf, img_shape, detections, seg_logits, box_results_list=None, ho
     return results
 
 
+_SIDE_STREAMS = {}
+_PINNED = {}      # pinned device->host staging buffers of train_forward, keyed by (net, slot, shape, dtype)
+
+
+def _side_stream(dev):
+    """one side stream per device for the GT<->anchor matching (kept out of the module so that nets stay picklable / deep-copyable)"""
+    key = (dev.type, dev.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
+
+
 # ------------------------------------------------------------------------------------------------------------------ net
 class net(nn.Module):
     """Retina U-Net.  `operate_stride1`/seg head follow cf (set cf.operate_stride1 False and num_seg_classes 0 for plain RetinaNet)."""
@@ -308,16 +320,14 @@ class net(nn.Module):
 
     def _to_host(self, tensors):
         """device tensors -> numpy through cached pinned staging buffers: all copies are queued, then ONE synchronisation"""
-        if not hasattr(self, '_pin'):
-            self._pin = {}
         outs = []
         for i, t in enumerate(tensors):
             t = t.detach().contiguous()
-            key = (i, tuple(t.shape), t.dtype)
-            buf = self._pin.get(key)
+            key = (id(self), i, tuple(t.shape), t.dtype)
+            buf = _PINNED.get(key)
             if buf is None:
                 buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=t.is_cuda)
-                self._pin[key] = buf
+                _PINNED[key] = buf
             buf.copy_(t, non_blocking=True)
             outs.append(buf)
         if tensors and tensors[0].is_cuda:
@@ -356,10 +366,9 @@ class net(nn.Module):
         # The matching synchronises with the host (exact-length positive lists, numpy sub-sampling).  On a side stream those waits cover only the
         # matching kernels, so the host is not held up by — and the GPU not drained of — the previous step's backward pass still in flight.
         main_stream = torch.cuda.current_stream(dev) if img.is_cuda else None
-        if main_stream is not None and getattr(self, '_match_stream', None) is None:
-            self._match_stream = torch.cuda.Stream(device=dev)
+        match_stream = _side_stream(dev) if main_stream is not None else None
         matched = []
-        with (torch.cuda.stream(self._match_stream) if main_stream is not None else contextlib.nullcontext()):
+        with (torch.cuda.stream(match_stream) if main_stream is not None else contextlib.nullcontext()):
             for b in range(n_b):
                 if len(gt_boxes[b]) > 0:
                     for ix in range(len(gt_boxes[b])):
@@ -370,7 +379,7 @@ class net(nn.Module):
                                     torch.zeros((cf.rpn_train_anchors_per_image, 2 * cf.dim), dtype=torch.float64, device=dev),
                                     torch.zeros(0, dtype=torch.long, device=dev)))
         if main_stream is not None:
-            main_stream.wait_stream(self._match_stream)        # the losses (main stream) consume the matching's tensors
+            main_stream.wait_stream(match_stream)              # the losses (main stream) consume the matching's tensors
             for tup in matched:
                 for t in tup:
                     t.record_stream(main_stream)
