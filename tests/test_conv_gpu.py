@@ -251,3 +251,26 @@ def test_bias_gradient_of_the_unfused_wgrad(cin, cout, sp):
     assert float((db.double() - ref).abs().max() / ref.abs().max()) < 1e-5
     ref_w = torch.einsum('ncdhw,nkdhw->ck', gy.double(), x.double()).reshape(cout, cin, 1, 1, 1)
     assert float((dw.double() - ref_w).abs().max() / ref_w.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad", [(36, 36, 3, (1, 1, 1), 1), (18, 18, 7, (2, 2, 1), 3)])
+def test_full_resolution_layers_vs_fp64(cin, cout, k, stride, pad):
+    """the two heaviest layers of cfg2 at their BASELINE size (2 x C x 128^3) against fp64 F.conv3d: forward, input gradient and weight gradient.
+    Weight gradients at this size sum 4.2 M products per element: the bound below (3e-5 of max|ref|, measured 9e-6) is what the accumulator
+    chain limit of the wgrad kernel (<= 512 MMAs per TMEM accumulator, partial sums combined in IEEE fp32) guarantees; 1e-4 is the parity bar."""
+    torch.manual_seed(11)
+    sp = (128, 128, 128)
+    k3, p3 = C._triple(k), C._triple(pad)
+    x = torch.randn(2, cin, *sp, device=DEV).contiguous(memory_format=torch.channels_last_3d)
+    w = torch.randn(cout, cin, *k3, device=DEV) / float(np.sqrt(cin * np.prod(k3)))
+    b = torch.randn(cout, device=DEV) * 0.1
+    y = C.conv3d_forward(x, w, b, stride, p3)
+    gy = torch.randn_like(y)
+    dx = C.conv3d_dgrad(gy, w, tuple(x.shape), stride, p3)
+    dw, db = C.conv3d_wgrad(x, gy, tuple(w.shape), stride, p3, True)
+    xd = x.double().contiguous().requires_grad_(True)          # NCDHW fp64 reference
+    wd, bd = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = F.conv3d(xd, wd, bd, stride=stride, padding=p3)
+    ref.backward(gy.double().contiguous())
+    errs = {"fprop": _rel(y, ref.detach()), "dgrad": _rel(dx, xd.grad), "wgrad": _rel(dw, wd.grad), "bias": _rel(db, bd.grad)}
+    assert errs["fprop"] < 3e-5 and errs["dgrad"] < 3e-5 and errs["wgrad"] < 3e-5 and errs["bias"] < 3e-5, errs
