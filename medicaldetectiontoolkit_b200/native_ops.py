@@ -311,7 +311,8 @@ class _SegLoss(torch.autograd.Function):
         lib = L.load()
         logits, target, sums = ctx.saved_tensors
         lay, n, vox, c, fpw, smooth = ctx.meta
-        gout = torch.stack([g_dice.reshape(()), g_ce.reshape(())]).to(torch.float32).contiguous()
+        zero = logits.new_zeros(())                      # an output that did not enter the loss arrives as None
+        gout = torch.stack([(g_dice if g_dice is not None else zero).reshape(()), (g_ce if g_ce is not None else zero).reshape(())]).to(torch.float32).contiguous()
         grad = torch.empty_strided(logits.shape, logits.stride(), dtype=torch.float32, device=logits.device)
         with torch.cuda.device(logits.device):
             L.check(lib.mdt_seg_loss_backward(L.ptr(logits), L.i64arr(lay), L.ptr(target), n, vox, c, fpw, smooth, L.ptr(sums), L.ptr(gout), L.ptr(grad),

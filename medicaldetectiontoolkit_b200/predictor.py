@@ -13,8 +13,6 @@ import torch
 
 from . import _lib as L
 
-_DEV = None
-
 
 def _device():
     if not torch.cuda.is_available():

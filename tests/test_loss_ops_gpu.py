@@ -169,3 +169,21 @@ def test_shem_pool_is_the_top_of_the_negatives():
     assert set(picked.tolist()) <= set(pool.tolist())
     want = (F.cross_entropy(logits[pos], match[pos].long()) + F.cross_entropy(logits[picked], torch.zeros(n_pos, dtype=torch.long, device=DEV))) / 2
     assert abs(loss.item() - want.item()) < 1e-5
+
+
+def test_seg_loss_single_term_backward():
+    """only one of the two outputs enters the loss: autograd hands None for the other (dice-only / CE-only configurations)"""
+    torch.manual_seed(9)
+    logits = torch.randn(1, 3, 8, 8, 8, device=DEV).requires_grad_(True)
+    seg = torch.randint(0, 3, (1, 8, 8, 8), device=DEV, dtype=torch.uint8)
+    dice, ce = native_ops.seg_loss(logits, seg)
+    (1 - dice).backward()
+    l64, dice_r, ce_r = _seg_reference(logits, seg)
+    (1 - dice_r).backward()
+    assert float((logits.grad.double() - l64.grad).abs().max() / l64.grad.abs().max()) < 1e-5
+    logits.grad = None
+    dice, ce = native_ops.seg_loss(logits, seg)
+    ce.backward()
+    l64, dice_r, ce_r = _seg_reference(logits, seg)
+    ce_r.backward()
+    assert float((logits.grad.double() - l64.grad).abs().max() / l64.grad.abs().max()) < 1e-5
