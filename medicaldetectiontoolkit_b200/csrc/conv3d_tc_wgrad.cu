@@ -11,8 +11,10 @@
 //    lo*hi + lo*lo in lanes [co_p, co_p + co); the epilogue adds both halves into dw.  (Used when 2 * co_p <= 128; otherwise 3 MMAs.)
 //
 // Work decomposition: a CTA owns up to CB "column blocks" (kd, kh, ci-chunk) whose accumulators fill its 512 TMEM columns, and a
-// strided share of the output lines; it streams dy lines + x halo lines through a 2-stage TMA ring and finally reduces its partial
-// dw with fp32 red.global.add.
+// strided share of the output lines; it streams dy lines + x halo lines through a 2-stage TMA ring and finally dumps its accumulators
+// (real channels only, no padding lanes / columns) to its slot of a partial buffer; wgrad_reduce_kernel adds the slots in a fixed order
+// (deterministic; the first version's fp32 red.global.add cost more than the MMAs).  The number of lines per CTA is bounded by the
+// accumulator chain limit (kMaxChain MMAs, see wg_splits): the tensor core's fp32 accumulation is not round-to-nearest.
 #include "conv3d_common.cuh"
 #include "tc_common.cuh"
 #include <cstdlib>
