@@ -262,6 +262,109 @@ bbox_overlaps_2D = bbox_overlaps
 bbox_overlaps_3D = bbox_overlaps
 
 
+# ---- the remaining small helpers of utils/model_utils.py (host-side numpy / eager torch; none of them is on the training hot path, they complete
+# the `mutils` surface that the reference's models, predictor and evaluator import)
+def compute_iou_2D(box, boxes, box_area, boxes_area):
+    """IoU of one box [y1, x1, y2, x2] with an array of boxes, areas passed in (utils/model_utils.py:35-54; no +1 extents)"""
+    return _np_iou(box, boxes, box_area, boxes_area, 2)
+
+
+def compute_iou_3D(box, boxes, box_volume, boxes_volume):
+    """3D twin, boxes [y1, x1, y2, x2, z1, z2] (utils/model_utils.py:58-79)"""
+    return _np_iou(box, boxes, box_volume, boxes_volume, 3)
+
+
+def _np_iou(box, boxes, vol, vols, dim):
+    box, boxes = np.asarray(box), np.asarray(boxes)
+    inter = np.maximum(np.minimum(box[3], boxes[:, 3]) - np.maximum(box[1], boxes[:, 1]), 0) * \
+        np.maximum(np.minimum(box[2], boxes[:, 2]) - np.maximum(box[0], boxes[:, 0]), 0)
+    if dim == 3:
+        inter = inter * np.maximum(np.minimum(box[5], boxes[:, 5]) - np.maximum(box[4], boxes[:, 4]), 0)
+    return inter / (vol + vols - inter)
+
+
+def compute_overlaps(boxes1, boxes2):
+    """IoU matrix [n1, n2] of two numpy box sets (utils/model_utils.py:83-110), one broadcast instead of the loop over boxes2; the per-element
+    expression and its operation order are the reference's, so the values are bit-identical"""
+    b1, b2 = np.asarray(boxes1), np.asarray(boxes2)
+    dim = b1.shape[1] // 2
+    v1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+    v2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+    a, b = b1[:, None, :], b2[None, :, :]
+    inter = np.maximum(np.minimum(b[..., 3], a[..., 3]) - np.maximum(b[..., 1], a[..., 1]), 0) * \
+        np.maximum(np.minimum(b[..., 2], a[..., 2]) - np.maximum(b[..., 0], a[..., 0]), 0)
+    if dim == 3:
+        v1 = v1 * (b1[:, 5] - b1[:, 4])
+        v2 = v2 * (b2[:, 5] - b2[:, 4])
+        inter = inter * np.maximum(np.minimum(b[..., 5], a[..., 5]) - np.maximum(b[..., 4], a[..., 4]), 0)
+    out = np.zeros((b1.shape[0], b2.shape[0]))
+    out[...] = inter / (v2[None, :] + v1[:, None] - inter)
+    return out
+
+
+def clip_boxes_numpy(boxes, window):
+    """clip [N, 4] / [N, 6] numpy boxes to the image (utils/model_utils.py:402-426).  As in the reference, y1 AND x1 are clipped to window[0]
+    and y2 AND x2 to window[1] (square in-plane patches make this the same as a per-axis clip); z to window[2]."""
+    boxes = np.asarray(boxes)
+    hi = [window[0], window[0], window[1], window[1]] + ([window[2], window[2]] if boxes.shape[1] == 6 else [])
+    return np.stack([np.clip(boxes[:, i], 0, hi[i]) for i in range(boxes.shape[1])], axis=1)
+
+
+def intersect1d(tensor1, tensor2):
+    """values present in both 1-D tensors, descending (utils/model_utils.py:667-670; both inputs hold unique values)"""
+    aux = torch.cat((tensor1, tensor2), dim=0).sort(descending=True)[0]
+    return aux[:-1][aux[1:] == aux[:-1]]
+
+
+def sum_tensor(input, axes, keepdim=False):
+    """sum over several axes (utils/model_utils.py:821-830)"""
+    axes = sorted(set(int(a) for a in np.unique(axes)))
+    return input.sum(dim=axes, keepdim=keepdim) if axes else input
+
+
+def get_dice_per_batch_and_class(pred, y, n_classes):
+    """hard dice per batch element and class of two label maps (b, 1, y, x, (z)) -> (b, c)   (utils/model_utils.py:803-818)"""
+    p, t = get_one_hot_encoding(pred, n_classes), get_one_hot_encoding(y, n_classes)
+    axes = tuple(range(2, p.ndim))
+    return 2.0 * np.sum(p * t, axis=axes) / (np.sum(p, axis=axes) + np.sum(t, axis=axes) + 1e-8)
+
+
+def batch_dice_mask(pred, y, mask, false_positive_weight=1.0, smooth=1e-6):
+    """batch_dice restricted to a pixel mask in 2D (utils/model_utils.py:863-890; the 3D branch of the reference ignores the mask and so does this)"""
+    if pred.dim() == 4:
+        m = mask.unsqueeze(1).expand(-1, pred.shape[1], -1, -1)
+        axes = (0, 2, 3)
+        intersect = (pred * y * m).sum(axes)
+        denom = (false_positive_weight * pred * m + y * m).sum(axes)
+    elif pred.dim() == 5:
+        axes = (0, 2, 3, 4)
+        intersect = (pred * y).sum(axes)
+        denom = (false_positive_weight * pred + y).sum(axes)
+    else:
+        raise ValueError('wrong input dimension in dice loss')
+    return torch.mean(((2 * intersect + smooth) / (denom + smooth))[1:])
+
+
+def unmold_mask_2D(mask, bbox, image_shape):
+    """small mask -> full-size image at its box, scipy linear zoom (utils/model_utils.py:147-163)"""
+    return _unmold(mask, [bbox[0], bbox[1]], [bbox[2], bbox[3]], tuple(image_shape[:2]))
+
+
+def unmold_mask_3D(mask, bbox, image_shape):
+    """3D twin (utils/model_utils.py:167-183)"""
+    return _unmold(mask, [bbox[0], bbox[1], bbox[4]], [bbox[2], bbox[3], bbox[5]], tuple(image_shape[:3]))
+
+
+def _unmold(mask, lo, hi, shape):
+    import scipy.ndimage
+    lo, hi = [int(v) for v in lo], [int(v) for v in hi]
+    full = np.zeros(shape)
+    size = [h - l for l, h in zip(lo, hi)]
+    z = scipy.ndimage.zoom(mask, [s / m for s, m in zip(size, mask.shape)], order=1).astype(np.float32)
+    full[tuple(slice(l, h) for l, h in zip(lo, hi))] = z
+    return full
+
+
 # Sampling mode of every stochastic draw on the path (SHEM pools, positive-roi sub-sampling): "random" = device RNG (the reference draws
 # from the CPU RNG: same distribution, different stream); "identity" = the permutation is the identity, i.e. the reference with
 # torch.randperm neutralised — the mode the reference-pinned parity tests run both sides in (tests/golden/make_model_golden.py).
