@@ -45,3 +45,49 @@ def test_no_oracle_in_product_path():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "libmdt_oracle" not in src and "import _oracle" not in src and "oracle/_ref" not in src, f
+
+
+def test_binding_arity_matches_the_header():
+    """ctypes never checks a prototype: count the parameters of every declaration in include/mdt_b200.h and compare with the bound argtypes
+    (a missing or extra argument would silently shift every later one)"""
+    text = open(os.path.join(ROOT, "include", "mdt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(mdt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 40
+    seen = set()
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert name in L.SIGNATURES, name
+        assert len(L.SIGNATURES[name][1]) == n, "%s: header declares %d parameters, the ctypes binding passes %d" % (name, n, len(L.SIGNATURES[name][1]))
+        seen.add(name)
+    assert seen == set(L.SIGNATURES)
+
+
+def test_binding_scalar_kinds_match_the_header():
+    """pointer / int / float / double / size_t / 64-bit of every parameter: a float bound where the header says double (or the reverse) passes
+    garbage without any error"""
+    text = open(os.path.join(ROOT, "include", "mdt_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    bad = []
+    for name, params in re.findall(r"\b(mdt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = " ".join(params.split())
+        if params in ("", "void"):
+            continue
+        for i, (decl, ct) in enumerate(zip(params.split(","), L.SIGNATURES[name][1])):
+            decl = decl.strip()
+            if "*" in decl:
+                ok = ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "_type_") and not issubclass(ct, ctypes._SimpleCData)
+            elif re.search(r"\bdouble\b", decl):
+                ok = ct is ctypes.c_double
+            elif re.search(r"\bfloat\b", decl):
+                ok = ct is ctypes.c_float
+            elif re.search(r"\bsize_t\b", decl):
+                ok = ct is ctypes.c_size_t
+            elif re.search(r"\blong long\b|\bint64_t\b", decl):
+                ok = ct in (ctypes.c_int64, ctypes.c_longlong)
+            else:
+                ok = ct in (ctypes.c_int, ctypes.c_uint)
+            if not ok:
+                bad.append((name, i, decl, ct))
+    assert not bad, bad
