@@ -133,3 +133,24 @@ def test_weight_init_equals_the_reference(model, init):
     finally:
         for k in [k for k in sys.modules if k == "cuda_functions" or k.startswith("cuda_functions.")]:
             del sys.modules[k]
+
+
+@pytest.mark.parametrize("model", ["ufrcnn", "detection_unet"])
+def test_other_reference_models_build_on_the_dropins(model):
+    """models/ufrcnn.py and models/detection_unet.py are outside the hot-path scope but share the import sites
+    (ufrcnn.py:24-27, the backbone path and mutils.NDConvGenerator): the unmodified reference files build entirely on libmdt_b200 modules"""
+    from medicaldetectiontoolkit_b200 import backbone as b200_backbone
+    from medicaldetectiontoolkit_b200 import conv as b200_conv
+    RS, mutils, saved, cf = _setup("mrcnn" if model == "ufrcnn" else "retina_unet")
+    try:
+        cf.model = model
+        if model == "ufrcnn":
+            cf.num_seg_classes, cf.operate_stride1, cf.frcnn_mode = 2, True, True
+        with RS.torch04_semantics(cpu=True):
+            net = RS.load_ref_module(model).net(cf, RS.Logger())
+        fpn = net.Fpn if hasattr(net, "Fpn") else net.fpn
+        assert os.path.samefile(fpn.__class__.__init__.__code__.co_filename, b200_backbone.__file__)
+        assert sum(isinstance(m, b200_conv.Conv3d) for m in net.modules()) > 60
+        assert sum(isinstance(m, torch.nn.Conv3d) for m in net.modules()) == 0
+    finally:
+        _teardown(mutils, saved)
