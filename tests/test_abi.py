@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from medicaldetectiontoolkit_b200 import _lib as L
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -91,3 +93,20 @@ def test_binding_scalar_kinds_match_the_header():
             if not ok:
                 bad.append((name, i, decl, ct))
     assert not bad, bad
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """the boundary is a C ABI: include/mdt_b200.h must compile as C99 (no C++-only constructs outside the extern "C" guards) and a C program
+    must link against the shared library and call a host-only entry point"""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mdt_b200.h"\n#include <stdio.h>\nint main(void) { printf("%d %s\\n", mdt_version(), mdt_error_string(-2)); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(L.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lmdt_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode()
+    assert out.split()[0] == str(L.load().mdt_version()) and "workspace" in out
