@@ -19,3 +19,5 @@ timeout 300 python tools/conv_profile.py > gpurun_out/conv_profile.txt 2>&1; hea
 timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; cut -c1-400 gpurun_out/bench.json; tail -3 gpurun_out/bench.err
 timeout 600 python bench.py --model mrcnn --steps 20 --warmup 5 > gpurun_out/bench_mrcnn.json 2> gpurun_out/bench_mrcnn.err; cut -c1-300 gpurun_out/bench_mrcnn.json
 MDT_REF_BUDGET_S=70 timeout 600 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-300 gpurun_out/bench_ref.json
+timeout 200 python tools/loss_bench.py > gpurun_out/loss_bench.json 2> gpurun_out/loss_bench.err; head -c 600 gpurun_out/loss_bench.json
+[ -n "$WITH_CUDNN" ] && timeout 400 python tools/cudnn_convs_bench.py --steps 5 --warmup 2 --kinds cudnn_fp32 cudnn_tf32 > gpurun_out/cudnn_convs.jsonl 2> gpurun_out/cudnn_convs.err; cat gpurun_out/cudnn_convs.jsonl 2>/dev/null
